@@ -1,0 +1,111 @@
+/* viquae_b200 — C ABI of the B200-native exact inner-product top-k + score-fusion engine.
+ *
+ * This is the drop-in boundary for the one hot path of PaulLerner/ViQuAE (meerqat) that the engine
+ * replaces: the FAISS IndexFlatIP object that meerqat.ir.search reaches through HF datasets.
+ * Each entry point names the reference interface it stands in for (paths relative to the reference
+ * checkout; `datasets/` is the HF datasets dependency, faiss is un-vendored third-party C++).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * error code (never throws); vq_last_error() gives the message for the calling thread.  An index is
+ * bound to one CUDA device and is thread-compatible, not thread-safe (the reference has a single
+ * caller thread: Dataset.map without num_proc, meerqat/ir/search.py:482).  Functions taking a
+ * `stream` enqueue asynchronously on it and do not synchronise; the *_host variants synchronise.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef VIQUAE_B200_H
+#define VIQUAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of vectors crossing the ABI */
+#define VQ_F32 0
+#define VQ_BF16 1
+#define VQ_F16 2
+
+/* error codes */
+#define VQ_OK 0
+#define VQ_ERR_CUDA (-1)        /* a CUDA runtime/driver call failed (see vq_last_error) */
+#define VQ_ERR_INVALID (-2)     /* bad argument (shape, dtype, k, null pointer) */
+#define VQ_ERR_UNSUPPORTED (-3) /* valid request the engine does not serve (e.g. k > 128) */
+#define VQ_ERR_NOMEM (-4)       /* workspace too small / allocation failed */
+
+/* kernel variants (vq_index_set_variant): 0 lets the engine choose from (dtype, nq) */
+#define VQ_VARIANT_AUTO 0
+#define VQ_VARIANT_TC_CG1 1   /* tcgen05 128x256 tiles, one CTA per SM */
+#define VQ_VARIANT_TC_CG2 2   /* tcgen05 cta_group::2, 256x256 tiles per CTA pair */
+#define VQ_VARIANT_STREAM 3   /* small-batch HBM-streaming kernel */
+
+typedef struct vq_index vq_index;
+
+/* Library / device probe.  Returns the number of CUDA devices (0 = none) or a negative error. */
+int vq_device_count(void);
+const char* vq_last_error(void);
+const char* vq_version(void);
+
+/* faiss.IndexFlat(d, faiss.METRIC_INNER_PRODUCT)            [datasets/search.py:276-288]
+ * `dtype` is the STORAGE type of the corpus on the device (VQ_F32 = exact mode, VQ_BF16 / VQ_F16 =
+ * tensor-core mode); `capacity` pre-sizes the device buffer in rows (it grows on demand). */
+int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capacity);
+void vq_index_destroy(vq_index* idx);
+
+/* faiss Index::add(n, x)                                    [datasets/search.py:311-313]
+ * x: [n, d] row-major, host or device pointer, element type src_dtype.  The engine copies, converts
+ * to the storage dtype and (l2norm != 0) L2-normalises rows on ingest, which is what the
+ * "L2norm,Flat" factory string does on add (meerqat/ir/search.py:230-245). */
+int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2norm, void* stream);
+
+/* faiss Index::ntotal / Index::d */
+uint64_t vq_index_ntotal(const vq_index* idx);
+int vq_index_dim(const vq_index* idx);
+int vq_index_dtype(const vq_index* idx);
+
+/* Row-sharding support: ids returned by search are local row + id_offset. */
+int vq_index_set_id_offset(vq_index* idx, int64_t id_offset);
+int vq_index_set_variant(vq_index* idx, int variant);
+
+/* faiss Index::reconstruct_n — copy rows [start, start+n) out as dst_dtype, [n, d] row-major,
+ * host or device destination.  Used by save/load (meerqat/ir/search.py:234-248). */
+int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* dst, int dst_dtype, void* stream);
+
+/* Bytes of device workspace vq_index_search needs for (nq, k) on this index. */
+size_t vq_index_workspace_bytes(const vq_index* idx, int nq, int k);
+
+/* faiss Index::search(n, x, k, D, I)                        [datasets/search.py:384; meerqat/ir/search.py:146]
+ * All pointers are DEVICE pointers.  q: [nq, d] of q_dtype; l2norm_q != 0 applies the reference's
+ * L2norm(queries) (meerqat/ir/search.py:43-46,144-145).  Outputs: out_scores float32 [nq, k] sorted
+ * descending, out_ids int64 [nq, k]; rows with fewer than k hits are padded with (-FLT_MAX, -1);
+ * equal scores are ordered by lower id.  Asynchronous on `stream`. */
+int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2norm_q, int k, float* out_scores,
+                    int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers — exactly the shape of faiss_index.search(queries, k) as HF datasets
+ * calls it with numpy arrays: float32 queries in, float32 scores / int64 ids out.  Host<->device
+ * copies and the engine-owned workspace are inside the call; returns after the results are on the host. */
+int vq_index_search_host(vq_index* idx, const float* q_host, int nq, int l2norm_q, int k, float* out_scores_host,
+                         int64_t* out_ids_host);
+
+/* Cross-GPU k-way merge after the all-gather of per-shard results.  Device pointers:
+ * scores float32 / ids int64 [n_lists, nq, k_in] (id < 0 = padding) -> [nq, k_out]. */
+int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out, float* out_scores,
+                  int64_t* out_ids, void* stream);
+
+/* meerqat.ir.fuse: default_minimum (fuse.py:132-149) -> normalisation (gzmuv fuse.py:86-129; ranx
+ * zmuv / min-max) -> ranx wsum -> descending sort, for n_runs dense runs of one query batch.
+ * Device pointers.  scores float64 / ids int64 [n_runs, nq, k_in] (id < 0 = absent entry);
+ * weights float64 [n_runs].  norm: 0 none, 1 zmuv, 2 gzmuv, 3 min-max.  Outputs: the fused union per
+ * query, out_scores float64 / out_ids int64 [nq, n_runs*k_in] sorted descending (padding -1),
+ * out_counts int32 [nq] = size of the union.  The union is NOT truncated to k, like ranx.fuse. */
+size_t vq_fuse_workspace_bytes(int n_runs, int nq, int k_in);
+int vq_fuse(const double* scores, const int64_t* ids, const double* weights, int n_runs, int nq, int k_in, int defmin,
+            int norm, double* out_scores, int64_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIQUAE_B200_H */

@@ -1,0 +1,369 @@
+// C ABI of the engine (include/viquae_b200.h): index object, kernel-variant dispatch, workspace carving.
+#include "../../include/viquae_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "vq_common.cuh"
+#include "vq_kernels.h"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) return fail(VQ_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct vq_index {
+    int d, dtype, device, ld, n_sms, variant;
+    uint64_t capacity, ntotal;
+    int64_t id_offset;
+    void* data;
+    // engine-owned buffers of the host-buffer entry point
+    void* hws;
+    size_t hws_bytes;
+};
+
+static size_t esize(int dtype) { return dtype == VQ_F32 ? 4 : 2; }
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static bool dtype_ok(int t) { return t == VQ_F32 || t == VQ_BF16 || t == VQ_F16; }
+
+extern "C" {
+
+const char* vq_last_error(void) { return g_err; }
+const char* vq_version(void) { return "viquae_b200 0.1 (sm_100a)"; }
+
+int vq_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capacity) {
+    if (!out || d <= 0 || !dtype_ok(dtype)) return fail(VQ_ERR_INVALID, "vq_index_create: bad arguments (d=%d dtype=%d)", d, dtype);
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VQ_ERR_INVALID, "vq_index_create: device %d not in [0, %d)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(VQ_ERR_UNSUPPORTED, "viquae_b200 needs an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
+    vq_index* idx = new vq_index();
+    idx->d = d;
+    idx->dtype = dtype;
+    idx->device = device;
+    idx->ld = dtype == VQ_F32 ? (d + 3) / 4 * 4 : (d + 7) / 8 * 8;  // 16-byte row stride (float4 / TMA)
+    idx->n_sms = prop.multiProcessorCount;
+    idx->variant = VQ_VARIANT_AUTO;
+    idx->capacity = 0;
+    idx->ntotal = 0;
+    idx->id_offset = 0;
+    idx->data = nullptr;
+    idx->hws = nullptr;
+    idx->hws_bytes = 0;
+    if (capacity) {
+        cudaError_t e = cudaMalloc(&idx->data, capacity * idx->ld * esize(dtype));
+        if (e != cudaSuccess) {
+            delete idx;
+            return fail(VQ_ERR_NOMEM, "vq_index_create: cudaMalloc of %llu rows failed: %s", (unsigned long long)capacity, cudaGetErrorString(e));
+        }
+        idx->capacity = capacity;
+    }
+    *out = idx;
+    return VQ_OK;
+}
+
+void vq_index_destroy(vq_index* idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    if (idx->data) cudaFree(idx->data);
+    if (idx->hws) cudaFree(idx->hws);
+    delete idx;
+}
+
+uint64_t vq_index_ntotal(const vq_index* idx) { return idx ? idx->ntotal : 0; }
+int vq_index_dim(const vq_index* idx) { return idx ? idx->d : 0; }
+int vq_index_dtype(const vq_index* idx) { return idx ? idx->dtype : -1; }
+
+int vq_index_set_id_offset(vq_index* idx, int64_t off) {
+    if (!idx) return fail(VQ_ERR_INVALID, "null index");
+    idx->id_offset = off;
+    return VQ_OK;
+}
+int vq_index_set_variant(vq_index* idx, int variant) {
+    if (!idx || variant < 0 || variant > 3) return fail(VQ_ERR_INVALID, "vq_index_set_variant: bad variant %d", variant);
+    idx->variant = variant;
+    return VQ_OK;
+}
+
+static int is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int grow(vq_index* idx, uint64_t need, cudaStream_t s) {
+    if (need <= idx->capacity) return VQ_OK;
+    uint64_t cap = idx->capacity ? idx->capacity : 1024;
+    while (cap < need) cap += cap / 2 + 1;
+    void* nd = nullptr;
+    const size_t row = (size_t)idx->ld * esize(idx->dtype);
+    cudaError_t e = cudaMalloc(&nd, cap * row);
+    if (e != cudaSuccess && cap > need) {  // retry with the exact size
+        cudaGetLastError();
+        cap = need;
+        e = cudaMalloc(&nd, cap * row);
+    }
+    if (e != cudaSuccess) return fail(VQ_ERR_NOMEM, "vq_index_add: cudaMalloc of %llu rows failed: %s", (unsigned long long)cap, cudaGetErrorString(e));
+    if (idx->ntotal) CUDA_TRY(cudaMemcpyAsync(nd, idx->data, idx->ntotal * row, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (idx->data) cudaFree(idx->data);
+    idx->data = nd;
+    idx->capacity = cap;
+    return VQ_OK;
+}
+
+int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2norm, void* stream) {
+    if (!idx || (!x && n) || !dtype_ok(src_dtype)) return fail(VQ_ERR_INVALID, "vq_index_add: bad arguments");
+    if (n == 0) return VQ_OK;
+    if (idx->ntotal + n > 0xFFFFFFFEull) return fail(VQ_ERR_UNSUPPORTED, "vq_index_add: more than 2^32-2 rows per shard");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    int rc = grow(idx, idx->ntotal + n, s);
+    if (rc) return rc;
+    const size_t row = (size_t)idx->ld * esize(idx->dtype);
+    uint8_t* dst = (uint8_t*)idx->data + idx->ntotal * row;
+    if (is_device_ptr(x)) {
+        rc = vq::prep_rows_launch(x, src_dtype, idx->d, dst, idx->dtype, idx->ld, (long long)n, idx->d, l2norm, s);
+        if (rc) return fail(VQ_ERR_CUDA, "vq_index_add: prep kernel launch failed (%d)", rc);
+    } else {
+        // host source: stage through a device buffer in 64 MB pieces, convert on the device
+        const size_t src_row = (size_t)idx->d * esize(src_dtype);
+        uint64_t chunk = (64ull << 20) / src_row;
+        if (chunk < 1) chunk = 1;
+        if (chunk > n) chunk = n;
+        void* stage = nullptr;
+        CUDA_TRY(cudaMalloc(&stage, chunk * src_row));
+        for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+            const uint64_t m = (n - r0 < chunk) ? n - r0 : chunk;
+            cudaError_t e = cudaMemcpyAsync(stage, (const uint8_t*)x + r0 * src_row, m * src_row, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) {
+                rc = vq::prep_rows_launch(stage, src_dtype, idx->d, dst + r0 * row, idx->dtype, idx->ld, (long long)m, idx->d, l2norm, s);
+                if (rc == 0) e = cudaStreamSynchronize(s);
+            }
+            if (e != cudaSuccess || rc) {
+                cudaFree(stage);
+                return fail(VQ_ERR_CUDA, "vq_index_add: host staging failed: %s (%d)", cudaGetErrorString(e), rc);
+            }
+        }
+        cudaFree(stage);
+    }
+    idx->ntotal += n;
+    return VQ_OK;
+}
+
+int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* dst, int dst_dtype, void* stream) {
+    if (!idx || (!dst && n) || !dtype_ok(dst_dtype) || start + n > idx->ntotal) return fail(VQ_ERR_INVALID, "vq_index_copy_rows: bad arguments");
+    if (n == 0) return VQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    const size_t row = (size_t)idx->ld * esize(idx->dtype);
+    const uint8_t* src = (const uint8_t*)idx->data + start * row;
+    if (is_device_ptr(dst)) {
+        int rc = vq::prep_rows_launch(src, idx->dtype, idx->ld, dst, dst_dtype, idx->d, (long long)n, idx->d, 0, s);
+        if (rc) return fail(VQ_ERR_CUDA, "vq_index_copy_rows: launch failed (%d)", rc);
+        return VQ_OK;
+    }
+    const size_t dst_row = (size_t)idx->d * esize(dst_dtype);
+    uint64_t chunk = (64ull << 20) / dst_row;
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    void* stage = nullptr;
+    CUDA_TRY(cudaMalloc(&stage, chunk * dst_row));
+    for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+        const uint64_t m = (n - r0 < chunk) ? n - r0 : chunk;
+        int rc = vq::prep_rows_launch(src + r0 * row, idx->dtype, idx->ld, stage, dst_dtype, idx->d, (long long)m, idx->d, 0, s);
+        cudaError_t e = rc ? cudaErrorUnknown : cudaMemcpyAsync((uint8_t*)dst + r0 * dst_row, stage, m * dst_row, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            cudaFree(stage);
+            return fail(VQ_ERR_CUDA, "vq_index_copy_rows: %s (%d)", cudaGetErrorString(e), rc);
+        }
+    }
+    cudaFree(stage);
+    return VQ_OK;
+}
+
+// ---- variant choice + workspace carving shared by workspace_bytes() and search()
+struct SearchPlan {
+    int kind;  // 0 = fp32 SIMT, 1 = tensor core, 2 = stream
+    vq::TcPlan tc;
+    vq::F32Plan f32;
+    vq::StreamPlan st;
+    int n_chunks, nq_pad;
+    size_t off_q, off_lists, off_counts, total;
+};
+
+static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
+    const long long n = (long long)idx->ntotal;
+    if (idx->dtype == VQ_F32) {
+        sp->kind = 0;
+        vq::f32_plan(nq, n, idx->n_sms, &sp->f32);
+        sp->n_chunks = sp->f32.n_chunks;
+        sp->nq_pad = sp->f32.nq_pad;
+    } else {
+        int variant = idx->variant;
+        if (variant == VQ_VARIANT_AUTO) variant = (nq <= 32) ? VQ_VARIANT_STREAM : (nq <= 128 ? VQ_VARIANT_TC_CG1 : VQ_VARIANT_TC_CG2);
+        if (variant == VQ_VARIANT_STREAM && nq > 32) variant = VQ_VARIANT_TC_CG1;
+        if (variant == VQ_VARIANT_STREAM) {
+            sp->kind = 2;
+            vq::stream_plan(nq, n, idx->n_sms, &sp->st);
+            sp->n_chunks = sp->st.n_chunks;
+            sp->nq_pad = sp->st.nq_pad;
+        } else {
+            sp->kind = 1;
+            vq::tc_plan(nq, n, idx->n_sms, variant == VQ_VARIANT_TC_CG2 ? 2 : 1, &sp->tc);
+            sp->n_chunks = sp->tc.n_chunks;
+            sp->nq_pad = sp->tc.nq_pad;
+        }
+    }
+    size_t off = 0;
+    sp->off_q = off;
+    off += align256((size_t)(nq > sp->nq_pad ? nq : sp->nq_pad) * idx->ld * esize(idx->dtype));
+    sp->off_lists = off;
+    off += align256((size_t)sp->n_chunks * sp->nq_pad * VQ_CAP * sizeof(uint64_t));
+    sp->off_counts = off;
+    off += align256((size_t)sp->n_chunks * sp->nq_pad * sizeof(int));
+    sp->total = off;
+}
+
+size_t vq_index_workspace_bytes(const vq_index* idx, int nq, int k) {
+    (void)k;
+    if (!idx || nq <= 0) return 0;
+    SearchPlan sp;
+    make_plan(idx, nq, &sp);
+    return sp.total;
+}
+
+int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2norm_q, int k, float* out_scores, int64_t* out_ids,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!idx || nq < 0 || k < 1 || !dtype_ok(q_dtype)) return fail(VQ_ERR_INVALID, "vq_index_search: bad arguments (nq=%d k=%d)", nq, k);
+    if (nq == 0) return VQ_OK;
+    if (!q || !out_scores || !out_ids || !workspace) return fail(VQ_ERR_INVALID, "vq_index_search: null pointer");
+    if (k > VQ_KMAX) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: k=%d > %d is not served by the fused top-k path", k, VQ_KMAX);
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    SearchPlan sp;
+    make_plan(idx, nq, &sp);
+    if (workspace_bytes < sp.total) return fail(VQ_ERR_NOMEM, "vq_index_search: workspace %zu < %zu bytes", workspace_bytes, sp.total);
+    uint8_t* ws = (uint8_t*)workspace;
+    void* qprep = ws + sp.off_q;
+    uint64_t* lists = (uint64_t*)(ws + sp.off_lists);
+    int* counts = (int*)(ws + sp.off_counts);
+    int rc = vq::prep_rows_launch(q, q_dtype, idx->d, qprep, idx->dtype, idx->ld, nq, idx->d, l2norm_q, s);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
+    if (idx->ntotal == 0) {
+        CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)sp.n_chunks * sp.nq_pad * sizeof(int), s));
+    } else if (sp.kind == 0) {
+        rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, (long long)idx->ntotal, idx->ld, idx->d, k,
+                                 sp.f32, lists, counts, s);
+    } else if (sp.kind == 1) {
+        rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, (long long)idx->ntotal, idx->ld, idx->d, idx->dtype, k, sp.tc, lists,
+                                counts, s);
+    } else {
+        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, (long long)idx->ntotal, idx->ld, idx->d, idx->dtype, k, sp.st, lists,
+                                    counts, s);
+    }
+    if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: kernel launch failed (%d: %s)", rc, rc < 0 && rc > -1000 ? cudaGetErrorString((cudaError_t)(-rc)) : "driver");
+    rc = vq::merge_lists_launch(lists, counts, sp.n_chunks, sp.nq_pad, nq, k, idx->id_offset, out_scores, (long long*)out_ids, s);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: merge launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+int vq_index_search_host(vq_index* idx, const float* q_host, int nq, int l2norm_q, int k, float* out_scores_host,
+                         int64_t* out_ids_host) {
+    if (!idx || nq < 0 || k < 1) return fail(VQ_ERR_INVALID, "vq_index_search_host: bad arguments");
+    if (nq == 0) return VQ_OK;
+    if (!q_host || !out_scores_host || !out_ids_host) return fail(VQ_ERR_INVALID, "vq_index_search_host: null pointer");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    SearchPlan sp;
+    make_plan(idx, nq, &sp);
+    const size_t q_bytes = align256((size_t)nq * idx->d * sizeof(float));
+    const size_t s_bytes = align256((size_t)nq * k * sizeof(float));
+    const size_t i_bytes = align256((size_t)nq * k * sizeof(int64_t));
+    const size_t need = q_bytes + s_bytes + i_bytes + sp.total;
+    if (idx->hws_bytes < need) {
+        if (idx->hws) cudaFree(idx->hws);
+        idx->hws = nullptr;
+        idx->hws_bytes = 0;
+        cudaError_t e = cudaMalloc(&idx->hws, need);
+        if (e != cudaSuccess) return fail(VQ_ERR_NOMEM, "vq_index_search_host: cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        idx->hws_bytes = need;
+    }
+    uint8_t* base = (uint8_t*)idx->hws;
+    float* dq = (float*)base;
+    float* ds = (float*)(base + q_bytes);
+    int64_t* di = (int64_t*)(base + q_bytes + s_bytes);
+    void* ws = base + q_bytes + s_bytes + i_bytes;
+    cudaStream_t s = 0;
+    CUDA_TRY(cudaMemcpyAsync(dq, q_host, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = vq_index_search(idx, dq, nq, VQ_F32, l2norm_q, k, ds, di, ws, sp.total, (void*)s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_scores_host, ds, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_ids_host, di, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return VQ_OK;
+}
+
+int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out, float* out_scores,
+                  int64_t* out_ids, void* stream) {
+    if (!scores || !ids || !out_scores || !out_ids || n_lists < 1 || nq < 0) return fail(VQ_ERR_INVALID, "vq_merge_topk: bad arguments");
+    int rc = vq::merge_topk_launch(scores, (const long long*)ids, n_lists, nq, k_in, k_out, out_scores, (long long*)out_ids, (cudaStream_t)stream);
+    if (rc == -2) return fail(VQ_ERR_UNSUPPORTED, "vq_merge_topk: k_in=%d k_out=%d not supported", k_in, k_out);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_merge_topk: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+size_t vq_fuse_workspace_bytes(int n_runs, int nq, int k_in) {
+    if (n_runs < 1 || nq < 1 || k_in < 1) return 0;
+    return vq::fuse_workspace_bytes(n_runs, nq, k_in);
+}
+
+int vq_fuse(const double* scores, const int64_t* ids, const double* weights, int n_runs, int nq, int k_in, int defmin, int norm,
+            double* out_scores, int64_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!scores || !ids || !weights || !out_scores || !out_ids || !out_counts || !workspace)
+        return fail(VQ_ERR_INVALID, "vq_fuse: null pointer");
+    vq::FuseParams fp;
+    fp.n_runs = n_runs;
+    fp.nq = nq;
+    fp.k_in = k_in;
+    fp.u_max = n_runs * k_in;
+    fp.defmin = defmin;
+    fp.norm = norm;
+    int rc = vq::fuse_launch(scores, (const long long*)ids, weights, fp, out_scores, (long long*)out_ids, out_counts, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
+    if (rc == -3) return fail(VQ_ERR_UNSUPPORTED, "vq_fuse: n_runs=%d k_in=%d norm=%d outside the supported range (n_runs*k_in <= 2048, n_runs <= 16)", n_runs, k_in, norm);
+    if (rc == -4) return fail(VQ_ERR_NOMEM, "vq_fuse: workspace too small");
+    if (rc) return fail(VQ_ERR_CUDA, "vq_fuse: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+}  // extern "C"

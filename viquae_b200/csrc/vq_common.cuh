@@ -1,0 +1,106 @@
+// Shared device-side pieces of the exact inner-product top-k engine (sm_100a only).
+//
+// Candidate keys.  Every (score, row) pair travels as ONE 64-bit key
+//     key = orderable(score) << 32 | ~row
+// so that "larger key" == "ranks earlier": higher score first, then LOWER row id (the tie rule the
+// oracle fixes; FAISS IndexFlat leaves it open).  Rows are shard-local uint32 (< 2^32 per GPU).
+//
+// Candidate lists.  Each (work item, query) owns a list of VQ_CAP keys in the caller-provided
+// workspace (HBM, L2-resident in practice).  Kernels append every score that beats the running
+// threshold; when a list could overflow, one warp sorts it (bitonic, registers + shuffles), keeps
+// the best k and raises the threshold to the k-th score.  Nothing above the true k-th score of
+// the slab is ever dropped, so the result is exact.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <float.h>
+#include <stdint.h>
+
+#define VQ_CAP 256   // keys per candidate list
+#define VQ_KMAX 128  // largest k served by the fused list path (VQ_CAP - VQ_KMAX >= 128 pushes per tile)
+#define VQ_FULL_MASK 0xffffffffu
+
+namespace vq {
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+    return __uint_as_float(u);
+}
+// s + 0.0f folds -0.0 into +0.0 so equal scores have equal keys
+__device__ __forceinline__ uint64_t make_key(float s, uint32_t row) {
+    return ((uint64_t)f2ord(s + 0.0f) << 32) | (uint32_t)(~row);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return ord2f((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_row(uint64_t k) { return ~(uint32_t)k; }
+
+__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// Bitonic sort, descending, of 32*E keys held E per lane; element e = r*32 + lane.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&key)[E], int lane) {
+#pragma unroll
+    for (int s = 2; s <= 32 * E; s <<= 1) {
+#pragma unroll
+        for (int j = s >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    if ((r & rj) == 0) {
+                        const bool desc = (((r * 32) & s) == 0);
+                        uint64_t a = key[r], b = key[r | rj];
+                        const bool sw = desc ? (a < b) : (a > b);
+                        key[r] = sw ? b : a;
+                        key[r | rj] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    const int e = r * 32 + lane;
+                    const uint64_t other = __shfl_xor_sync(VQ_FULL_MASK, key[r], j);
+                    const bool lower = (lane & j) == 0;
+                    const bool desc = ((e & s) == 0);
+                    key[r] = (lower == desc) ? umax64(key[r], other) : umin64(key[r], other);
+                }
+            }
+        }
+    }
+}
+
+// Warp-cooperative prune of one candidate list: sort its n (<= VQ_CAP) keys, keep the best
+// min(n, k) in place (sorted descending), return the new length.  thr_out = k-th score if the
+// list held at least k keys, else -FLT_MAX.  Called by all 32 lanes with identical arguments.
+__device__ __forceinline__ int warp_prune_list(uint64_t* list, int n, int k, int lane, float& thr_out) {
+    uint64_t key[VQ_CAP / 32];
+#pragma unroll
+    for (int r = 0; r < VQ_CAP / 32; r++) {
+        const int e = r * 32 + lane;
+        key[r] = (e < n) ? __ldcg(reinterpret_cast<const unsigned long long*>(list) + e) : 0ull;
+    }
+    warp_bitonic_sort_desc<VQ_CAP / 32>(key, lane);
+    const int m = n < k ? n : k;
+#pragma unroll
+    for (int r = 0; r < VQ_KMAX / 32; r++) {
+        const int e = r * 32 + lane;
+        if (e < m) __stcg(reinterpret_cast<unsigned long long*>(list) + e, (unsigned long long)key[r]);
+    }
+    uint64_t kth = 0;
+    const int rk = (k - 1) >> 5, lk = (k - 1) & 31;
+#pragma unroll
+    for (int r = 0; r < VQ_KMAX / 32; r++) {
+        const uint64_t t = __shfl_sync(VQ_FULL_MASK, key[r], lk);
+        if (r == rk) kth = t;
+    }
+    thr_out = (n >= k) ? key_score(kth) : -FLT_MAX;
+    __syncwarp();
+    return m;
+}
+
+}  // namespace vq

@@ -1,0 +1,312 @@
+// K5 — late fusion of the per-index runs of one query batch (meerqat.ir.fuse), in float64 like the
+// reference (numba typed dicts unicode -> float64, meerqat/ir/fuse.py:54-57).
+//
+//   default_minimum  fuse.py:132-149  per query, U = union of doc ids over runs; every run that has at
+//                                     least one result for the query gets its missing docs filled with
+//                                     that run's per-query minimum.  Happens BEFORE normalisation.
+//   gzmuv            fuse.py:86-129   s' = (s - mu) / max(sigma, 1e-9) with mu / sigma (population)
+//                                     over ALL scores of the run (all queries, filled entries included)
+//   zmuv, min-max    ranx norms       same formula per (run, query) / (s - min) / max(max - min, 1e-9)
+//   wsum             ranx.fuse        fused(d) = sum_r w_r * s'_r(d) over the runs that hold d
+//   result                            union per query sorted by descending fused score (ties: lower id)
+//
+// Three small kernels: A builds the union and the filled [U x R] matrix per query (sort by doc id in
+// shared memory), B reduces the global statistics per run (gzmuv only; fixed-order tree, two-pass
+// variance like np.std), C normalises, combines and sorts.  Latency/HBM-bound and tiny next to K3.
+#include "vq_common.cuh"
+#include "vq_kernels.h"
+
+#include <math.h>
+
+namespace vq {
+namespace fuse {
+
+constexpr int THREADS = 256;
+constexpr int E_MAX = 2048;   // n_runs * k_in entries per query (48 KB static smem budget)
+constexpr int R_MAX = 16;
+
+__device__ __forceinline__ void sort_desc_u64(uint64_t* keys, int S) {
+    for (int s = 2; s <= S; s <<= 1)
+        for (int j = s >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (S >> 1); i += THREADS) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                const bool desc = (lo & s) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if (desc ? (a < b) : (a > b)) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+}
+
+// "a ranks before b": larger key, then smaller id
+__device__ __forceinline__ bool before(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
+    return ka > kb || (ka == kb && ia < ib);
+}
+__device__ __forceinline__ void sort_pairs_desc(uint64_t* keys, uint32_t* vals, int S) {
+    for (int s = 2; s <= S; s <<= 1)
+        for (int j = s >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (S >> 1); i += THREADS) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                const bool desc = (lo & s) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                const uint32_t va = vals[lo], vb = vals[hi];
+                const bool sw = desc ? before(b, vb, a, va) : before(a, va, b, vb);
+                if (sw) { keys[lo] = b; keys[hi] = a; vals[lo] = vb; vals[hi] = va; }
+            }
+            __syncthreads();
+        }
+}
+
+__device__ __forceinline__ int pow2_ge(int x) { int p = 2; while (p < x) p <<= 1; return p; }
+
+__device__ __forceinline__ uint64_t d2ord(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v + 0.0);
+    return u ^ ((u >> 63) ? ~0ull : (1ull << 63));
+}
+
+// fixed-order block reductions (result broadcast to all threads)
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_min(double v, double* red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+
+// ---- A: union of doc ids + filled matrix.  mat[q][u][r] (NaN = run r does not hold doc u), doc[q][u], ucount[q]
+__global__ void __launch_bounds__(THREADS)
+union_kernel(const double* __restrict__ scores, const long long* __restrict__ ids, int R, int nq, int k_in, int defmin,
+             double* __restrict__ mat, long long* __restrict__ doc, int* __restrict__ ucount) {
+    __shared__ uint64_t keys[E_MAX];
+    __shared__ double red[THREADS];
+    __shared__ int scan[THREADS];
+    __shared__ double run_min[R_MAX];
+    __shared__ int run_n[R_MAX];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int E = R * k_in, S = pow2_ge(E);
+    // per-run minimum and count over the entries present for this query
+    for (int r = 0; r < R; r++) {
+        double mn = INFINITY;
+        double n = 0.0;
+        for (int i = tid; i < k_in; i += THREADS) {
+            const size_t at = ((size_t)r * nq + q) * k_in + i;
+            if (ids[at] >= 0) { mn = fmin(mn, scores[at]); n += 1.0; }
+        }
+        mn = block_min(mn, red);
+        n = block_sum(n, red);
+        if (tid == 0) { run_min[r] = mn; run_n[r] = (int)n; }
+    }
+    // sort present entries by doc id: key = ~(id << 32 | run << 16 | slot); absent -> 0 (sorts last)
+    for (int e = tid; e < S; e += THREADS) {
+        uint64_t key = 0ull;
+        if (e < E) {
+            const int r = e / k_in, slot = e - r * k_in;
+            const long long id = ids[((size_t)r * nq + q) * k_in + slot];
+            if (id >= 0) key = ~(((uint64_t)(uint32_t)id << 32) | ((uint64_t)r << 16) | (uint64_t)slot);
+        }
+        keys[e] = key;
+    }
+    __syncthreads();
+    sort_desc_u64(keys, S);
+    // head flags -> exclusive scan -> union index of every entry (each thread owns a contiguous span)
+    const int span = (S + THREADS - 1) / THREADS;
+    const int b0 = tid * span, b1 = min(S, b0 + span);
+    int local = 0;
+    for (int i = b0; i < b1; i++) {
+        const uint64_t key = keys[i];
+        if (key == 0ull) break;
+        const uint32_t id = (uint32_t)((~key) >> 32);
+        const bool head = (i == 0) || ((uint32_t)((~keys[i - 1]) >> 32) != id);
+        local += head ? 1 : 0;
+    }
+    scan[tid] = local;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < THREADS; i++) { const int v = scan[i]; scan[i] = run; run += v; }
+        ucount[q] = run;
+    }
+    __syncthreads();
+    const int U = ucount[q];
+    const size_t mbase = (size_t)q * E * R;
+    for (int i = tid; i < U * R; i += THREADS) {
+        const int r = i % R;
+        mat[mbase + i] = (defmin && run_n[r] > 0) ? run_min[r] : nan("");
+    }
+    __syncthreads();
+    int u = scan[tid] - 1;
+    for (int i = b0; i < b1; i++) {
+        const uint64_t key = keys[i];
+        if (key == 0ull) break;
+        const uint64_t k2 = ~key;
+        const uint32_t id = (uint32_t)(k2 >> 32);
+        const int r = (int)((k2 >> 16) & 0xFFFF), slot = (int)(k2 & 0xFFFF);
+        const bool head = (i == 0) || ((uint32_t)((~keys[i - 1]) >> 32) != id);
+        if (head) { u++; doc[(size_t)q * E + u] = (long long)id; }
+        mat[mbase + (size_t)u * R + r] = scores[((size_t)r * nq + q) * k_in + slot];
+    }
+}
+
+// ---- B: global mean / population std per run over all queries (gzmuv)
+__global__ void __launch_bounds__(THREADS)
+gstats_kernel(const double* __restrict__ mat, const int* __restrict__ ucount, int R, int nq, int E, double* __restrict__ gstats) {
+    __shared__ double red[THREADS];
+    const int r = blockIdx.x;
+    double s = 0.0, n = 0.0;
+    for (int q = 0; q < nq; q++) {
+        const int U = ucount[q];
+        const double* m = mat + (size_t)q * E * R;
+        for (int u = threadIdx.x; u < U; u += THREADS) {
+            const double v = m[(size_t)u * R + r];
+            if (!isnan(v)) { s += v; n += 1.0; }
+        }
+    }
+    s = block_sum(s, red);
+    n = block_sum(n, red);
+    const double mean = n > 0.0 ? s / n : 0.0;
+    double ss = 0.0;
+    for (int q = 0; q < nq; q++) {
+        const int U = ucount[q];
+        const double* m = mat + (size_t)q * E * R;
+        for (int u = threadIdx.x; u < U; u += THREADS) {
+            const double v = m[(size_t)u * R + r];
+            if (!isnan(v)) ss += (v - mean) * (v - mean);
+        }
+    }
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) {
+        gstats[2 * r] = mean;
+        gstats[2 * r + 1] = n > 0.0 ? sqrt(ss / n) : 0.0;
+    }
+}
+
+// ---- C: normalise + weighted sum + sort
+__global__ void __launch_bounds__(THREADS)
+combine_kernel(const double* __restrict__ mat, const long long* __restrict__ doc, const int* __restrict__ ucount,
+               const double* __restrict__ weights, const double* __restrict__ gstats, int R, int nq, int E, int norm,
+               double* __restrict__ out_scores, long long* __restrict__ out_ids, int* __restrict__ out_counts) {
+    __shared__ uint64_t keys[E_MAX];
+    __shared__ uint32_t vals[E_MAX];
+    __shared__ double red[THREADS];
+    __shared__ double sub[R_MAX], div[R_MAX];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int U = ucount[q];
+    const double* m = mat + (size_t)q * E * R;
+    for (int r = 0; r < R; r++) {
+        double a = 0.0, b = 1.0;
+        if (norm == 1) {  // zmuv over this query's entries of run r
+            double s = 0.0, n = 0.0;
+            for (int u = tid; u < U; u += THREADS) { const double v = m[(size_t)u * R + r]; if (!isnan(v)) { s += v; n += 1.0; } }
+            s = block_sum(s, red);
+            n = block_sum(n, red);
+            const double mean = n > 0.0 ? s / n : 0.0;
+            double ss = 0.0;
+            for (int u = tid; u < U; u += THREADS) { const double v = m[(size_t)u * R + r]; if (!isnan(v)) ss += (v - mean) * (v - mean); }
+            ss = block_sum(ss, red);
+            a = mean;
+            b = fmax(n > 0.0 ? sqrt(ss / n) : 0.0, 1e-9);
+        } else if (norm == 2) {
+            a = gstats[2 * r];
+            b = fmax(gstats[2 * r + 1], 1e-9);
+        } else if (norm == 3) {
+            double mn = INFINITY, mx = -INFINITY;
+            for (int u = tid; u < U; u += THREADS) { const double v = m[(size_t)u * R + r]; if (!isnan(v)) { mn = fmin(mn, v); mx = fmax(mx, v); } }
+            mn = block_min(mn, red);
+            mx = block_max(mx, red);
+            a = mn;
+            b = fmax(mx - mn, 1e-9);
+        }
+        if (tid == 0) { sub[r] = a; div[r] = b; }
+    }
+    __syncthreads();
+    const int S = pow2_ge(U);
+    for (int u = tid; u < S; u += THREADS) {
+        uint64_t key = 0ull;
+        uint32_t val = 0xFFFFFFFFu;
+        if (u < U) {
+            double f = 0.0;
+            for (int r = 0; r < R; r++) {
+                const double v = m[(size_t)u * R + r];
+                if (!isnan(v)) f += weights[r] * ((v - sub[r]) / div[r]);
+            }
+            key = d2ord(f);
+            val = (uint32_t)doc[(size_t)q * E + u];
+        }
+        keys[u] = key;
+        vals[u] = val;
+    }
+    __syncthreads();
+    sort_pairs_desc(keys, vals, S);
+    for (int i = tid; i < E; i += THREADS) {
+        if (i < U) {
+            const uint64_t o = keys[i];
+            const unsigned long long bits = (o >> 63) ? (o ^ (1ull << 63)) : ~o;
+            out_scores[(size_t)q * E + i] = __longlong_as_double((long long)bits);
+            out_ids[(size_t)q * E + i] = (long long)vals[i];
+        } else {
+            out_scores[(size_t)q * E + i] = 0.0;
+            out_ids[(size_t)q * E + i] = -1;
+        }
+    }
+    if (tid == 0) out_counts[q] = U;
+}
+
+}  // namespace fuse
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t fuse_workspace_bytes(int n_runs, int nq, int k_in) {
+    const size_t E = (size_t)n_runs * k_in;
+    return align256((size_t)nq * E * n_runs * sizeof(double)) + align256((size_t)nq * E * sizeof(long long)) +
+           align256((size_t)nq * sizeof(int)) + align256((size_t)2 * n_runs * sizeof(double));
+}
+
+int fuse_launch(const double* scores, const long long* ids, const double* weights, const FuseParams& fp,
+                double* out_scores, long long* out_ids, int* out_counts, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    const int R = fp.n_runs, nq = fp.nq, k_in = fp.k_in;
+    const int E = R * k_in;
+    if (R < 1 || R > fuse::R_MAX || k_in < 1 || k_in > 65535 || E > fuse::E_MAX || fp.norm < 0 || fp.norm > 3) return -3;
+    if (nq <= 0) return 0;
+    if (ws_bytes < fuse_workspace_bytes(R, nq, k_in)) return -4;
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    double* mat = reinterpret_cast<double*>(w);
+    w += align256((size_t)nq * E * R * sizeof(double));
+    long long* doc = reinterpret_cast<long long*>(w);
+    w += align256((size_t)nq * E * sizeof(long long));
+    int* ucount = reinterpret_cast<int*>(w);
+    w += align256((size_t)nq * sizeof(int));
+    double* gstats = reinterpret_cast<double*>(w);
+    fuse::union_kernel<<<nq, fuse::THREADS, 0, stream>>>(scores, ids, R, nq, k_in, fp.defmin, mat, doc, ucount);
+    if (fp.norm == 2) fuse::gstats_kernel<<<R, fuse::THREADS, 0, stream>>>(mat, ucount, R, nq, E, gstats);
+    fuse::combine_kernel<<<nq, fuse::THREADS, 0, stream>>>(mat, doc, ucount, weights, gstats, R, nq, E, fp.norm, out_scores, out_ids, out_counts);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+}  // namespace vq

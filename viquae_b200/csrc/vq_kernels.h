@@ -1,0 +1,74 @@
+// Internal launch interfaces between the C-ABI layer (vq_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VQ_DTYPE_F32 0
+#define VQ_DTYPE_BF16 1
+#define VQ_DTYPE_F16 2
+
+namespace vq {
+
+// ---- K0: ingest / query preparation (vq_prep.cu)
+// src [n, d] (src_dtype, row stride ld_src) -> dst [n, ld_dst] (dst_dtype); optional row L2-normalisation;
+// columns d..ld_dst-1 are zero-filled.
+int prep_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
+                     long long n, int d, int l2norm, cudaStream_t stream);
+
+// ---- K3: tensor-core contraction + fused top-k (vq_tc.cu)
+struct TcPlan {
+    int cg;               // CTAs per cluster (1 or 2)
+    int m_tiles;          // query tiles of 128*cg
+    int n_tiles;          // corpus tiles of 256 rows
+    int n_chunks;         // corpus slabs; work item = (m_tile, chunk)
+    int tiles_per_chunk;
+    int nq_pad;           // m_tiles * 128 * cg
+    int n_clusters;       // persistent clusters launched
+};
+struct TcParams {
+    uint64_t* lists;      // [n_chunks][nq_pad][VQ_CAP] candidate keys
+    int* counts;          // [n_chunks][nq_pad]
+    long long n_rows;
+    int nq, nq_pad, k, num_kb, m_tiles, n_tiles, n_chunks, tiles_per_chunk;
+    uint32_t idesc_base;
+};
+void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan);
+int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
+                   const TcPlan& plan, uint64_t* lists, int* counts, cudaStream_t stream);
+
+// ---- K1: fp32 exact SIMT contraction + fused top-k (vq_fp32.cu)
+struct F32Plan {
+    int m_tiles, n_tiles, n_chunks, tiles_per_chunk, nq_pad, n_ctas;
+};
+void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan);
+int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
+                    const F32Plan& plan, uint64_t* lists, int* counts, cudaStream_t stream);
+
+// ---- K2: small-batch HBM-streaming contraction + fused top-k (vq_stream.cu)
+struct StreamPlan {
+    int n_ctas, nq_pad, n_chunks;
+    long long rows_per_cta;
+};
+void stream_plan(int nq, long long n_rows, int n_sms, StreamPlan* plan);
+int stream_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
+                       const StreamPlan& plan, uint64_t* lists, int* counts, cudaStream_t stream);
+
+// ---- K4: merges (vq_merge.cu)
+// candidate-key lists [n_chunks][nq_pad][VQ_CAP] (+counts) -> final [nq][k] scores (f32) / ids (i64, + id_offset)
+int merge_lists_launch(const uint64_t* lists, const int* counts, int n_chunks, int nq_pad, int nq, int k, long long id_offset,
+                       float* out_scores, long long* out_ids, cudaStream_t stream);
+// per-shard results [n_lists][nq][k_in] (scores f32, ids i64; id < 0 = padding) -> [nq][k_out]
+int merge_topk_launch(const float* scores, const long long* ids, int n_lists, int nq, int k_in, int k_out,
+                      float* out_scores, long long* out_ids, cudaStream_t stream);
+
+// ---- K5: score fusion (vq_fuse.cu)
+struct FuseParams {
+    int n_runs, nq, k_in, u_max;
+    int defmin;       // fill missing docs with the run's per-query minimum (meerqat/ir/fuse.py:132-149)
+    int norm;         // 0 none, 1 zmuv (per query), 2 gzmuv (global, fuse.py:86-129), 3 min-max
+};
+size_t fuse_workspace_bytes(int n_runs, int nq, int k_in);
+int fuse_launch(const double* scores, const long long* ids, const double* weights, const FuseParams& fp,
+                double* out_scores, long long* out_ids, int* out_counts, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace vq

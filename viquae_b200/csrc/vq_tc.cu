@@ -1,0 +1,479 @@
+// K3 — bf16/fp16 query x corpus contraction on the 5th-gen tensor cores with a fused top-k.
+//
+// Replaces faiss IndexFlat(d, METRIC_INNER_PRODUCT)::search as reached from
+// meerqat/ir/search.py:146 -> datasets/search.py:384 for 16-bit corpora.  The score matrix never
+// reaches HBM: every 128(query) x 256(corpus row) tile is accumulated in TMEM by tcgen05.mma
+// (operands staged in shared memory by TMA, 128-byte swizzle), read back with tcgen05.ld by four
+// epilogue warps, and filtered against a per-query running threshold held in a register.
+//
+// Layout of one tile:  D[M = queries, N = corpus rows] = Q[M, K] . X[N, K]^T, both operands K-major.
+// Queries sit on the TMEM *lanes*, so one epilogue thread owns one query: its threshold and its
+// candidate count live in registers and the 256 scores of a tile stream past it column by column.
+//
+// CG = 1: one CTA per SM, UMMA 128x256x16.   CG = 2: a CTA pair (cluster of 2) issues
+// tcgen05.mma.cta_group::2 with UMMA 256x256x16: each CTA holds 128 queries and HALF of the corpus
+// tile, halving the L2->SM corpus traffic per query row.
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM
+// allocator, warp 3 idle, warps 4..7 epilogue (TMEM lane quarter = warp % 4).
+#include "vq_common.cuh"
+#include "vq_kernels.h"
+
+#include <cuda.h>
+
+namespace vq {
+namespace tc {
+
+constexpr int BLOCK_Q = 128;   // queries per CTA (TMEM lanes)
+constexpr int BLOCK_N = 256;   // corpus rows per tile (UMMA_N, TMEM columns)
+constexpr int BLOCK_K = 64;    // 64 x 2 B = one 128-byte swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int ACC_STAGES = 2;  // 2 x 256 columns = all 512 TMEM columns
+constexpr int THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr uint32_t A_STAGE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KB
+
+template <int CG> struct Cfg {
+    static constexpr int LOAD_N = BLOCK_N / CG;                       // corpus rows each CTA loads
+    static constexpr uint32_t B_STAGE_BYTES = LOAD_N * BLOCK_K * 2;   // 32 KB / 16 KB
+    static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (CG == 1) ? 4 : 6;                  // 192 KB of operand ring
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster (works for cta == self)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 remAddr32;\n"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* p) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(p) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* smem, int c0, int c1, uint64_t hint) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+            "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+            : "memory");
+    } else {
+        // both CTAs of the pair execute this; clearing the peer bit routes complete_tx to the leader's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+            "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG> __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// tcgen05.commit: the mbarrier gets one arrival once all MMAs issued so far by this thread are done
+template <int CG> __device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: 8-row groups are 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // SBO
+    d |= (uint64_t)1 << 46;                    // descriptor version
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+
+// ----------------------------------------------------------------------------- the kernel
+template <int CG>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, TcParams p) {
+    using C = Cfg<CG>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + C::STAGES;
+    uint64_t* tmem_full_bar = bars + 2 * C::STAGES;
+    uint64_t* tmem_empty_bar = bars + 2 * C::STAGES + ACC_STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 1) ? 0u : cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x / CG;
+    const int n_clusters = gridDim.x / CG;
+
+    if (CG > 1) cluster_sync_all();
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::STAGES; i++) {
+            mbar_init(&full_bar[i], CG);   // one arrival per CTA producer (all land on the leader)
+            mbar_init(&empty_bar[i], 1);   // one tcgen05.commit
+        }
+        for (int i = 0; i < ACC_STAGES; i++) {
+            mbar_init(&tmem_full_bar[i], 1);        // one tcgen05.commit
+            mbar_init(&tmem_empty_bar[i], CG * 4);  // one arrival per epilogue warp of each CTA
+        }
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc<CG>(tmem_ptr_smem, 512);
+    }
+    tc_fence_before();
+    if (CG > 1) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_kb = p.num_kb;
+    const int n_items = p.m_tiles * p.n_chunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one lane; both CTAs of a pair) =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int m_tile = item % p.m_tiles, chunk = item / p.m_tiles;
+                const int q_row0 = (m_tile * CG + (int)rank) * BLOCK_Q;
+                const int t0 = chunk * p.tiles_per_chunk;
+                const int t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+                for (int t = t0; t < t1; t++) {
+                    const int x_row0 = t * BLOCK_N + (int)rank * C::LOAD_N;
+                    for (int kb = 0; kb < num_kb; kb++) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        tma_load_2d<CG>(&tmap_q, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, q_row0,
+                                        0x14F0000000000000ull /*evict last: queries are re-read by every tile*/);
+                        tma_load_2d<CG>(&tmap_x, &full_bar[stage], smem_b + stage * C::B_STAGE_BYTES, kb * BLOCK_K, x_row0,
+                                        0x1000000000000000ull /*evict normal*/);
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
+                        else mbar_arrive_cluster(&full_bar[stage], 0);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread of the leader CTA) =====================
+        if (leader && lane == 0) {
+            const uint32_t idesc = p.idesc_base | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((BLOCK_Q * CG) >> 4) << 24);
+            uint32_t stage = 0, phase = 0, iter = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int chunk = item / p.m_tiles;
+                const int t0 = chunk * p.tiles_per_chunk;
+                const int t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+                for (int t = t0; t < t1; t++, iter++) {
+                    const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+                    mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                    for (int kb = 0; kb < num_kb; kb++) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
+#pragma unroll
+                        for (int k4 = 0; k4 < BLOCK_K / UMMA_K; k4++) {
+                            // +32 B per UMMA_K inside the swizzle atom = +2 in the (addr >> 4) field
+                            umma_f16<CG>(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc, (uint32_t)((kb | k4) != 0));
+                        }
+                        umma_commit<CG>(&empty_bar[stage]);                       // frees the smem slot (both CTAs)
+                        if (kb == num_kb - 1) umma_commit<CG>(&tmem_full_bar[as]);  // accumulator ready (both CTAs)
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue: TMEM -> registers -> threshold filter -> candidate lists =====================
+        const int ew = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quarter this warp may read
+        const uint32_t lane_field = (uint32_t)(ew * 32) << 16;
+        const int k = p.k;
+        uint32_t iter = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int m_tile = item % p.m_tiles, chunk = item / p.m_tiles;
+            const int q = (m_tile * CG + (int)rank) * BLOCK_Q + ew * 32 + lane;  // this thread's query
+            const int q0_warp = q - lane;
+            uint64_t* warp_lists = p.lists + ((size_t)chunk * p.nq_pad + q0_warp) * VQ_CAP;
+            unsigned long long* my_list = reinterpret_cast<unsigned long long*>(warp_lists + (size_t)lane * VQ_CAP);
+            const bool active = q < p.nq;
+            int cnt = 0;
+            float thr = active ? -FLT_MAX : INFINITY;
+            const int t0 = chunk * p.tiles_per_chunk;
+            const int t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+            for (int t = t0; t < t1; t++, iter++) {
+                const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+                mbar_wait(&tmem_full_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t row0 = (uint32_t)t * BLOCK_N;
+                const int n_valid = (int)min((long long)BLOCK_N, p.n_rows - (long long)row0);
+#pragma unroll 1
+                for (int cb = 0; cb < BLOCK_N / 32; cb++) {
+                    // make room: a 32-column block can append at most 32 keys to a list
+                    unsigned need = __ballot_sync(VQ_FULL_MASK, cnt > VQ_CAP - 32);
+                    while (need) {
+                        const int l = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int n_l = __shfl_sync(VQ_FULL_MASK, cnt, l);
+                        float thr_l;
+                        const int m_l = warp_prune_list(warp_lists + (size_t)l * VQ_CAP, n_l, k, lane, thr_l);
+                        if (lane == l) { cnt = m_l; thr = thr_l; }
+                    }
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_field + as * BLOCK_N + cb * 32, v);
+                    tmem_ld_wait();
+                    if (cb == BLOCK_N / 32 - 1) {
+                        // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                    }
+                    const uint32_t rbase = row0 + cb * 32;
+                    if (cb * 32 + 32 <= n_valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float s = __uint_as_float(v[j]);
+                            if (s > thr) {
+                                __stcg(my_list + cnt, (unsigned long long)make_key(s, rbase + j));
+                                cnt++;
+                            }
+                        }
+                    } else {
+                        const int lim = n_valid - cb * 32;  // rows past the end of the corpus are TMA zero fill
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float s = __uint_as_float(v[j]);
+                            if (j < lim && s > thr) {
+                                __stcg(my_list + cnt, (unsigned long long)make_key(s, rbase + j));
+                                cnt++;
+                            }
+                        }
+                    }
+                }
+            }
+            // end of the work item: every list is sorted, cut to k, and its length published
+            __syncwarp();
+            for (int l = 0; l < 32; l++) {
+                const int n_l = __shfl_sync(VQ_FULL_MASK, cnt, l);
+                float thr_l;
+                const int m_l = warp_prune_list(warp_lists + (size_t)l * VQ_CAP, n_l, k, lane, thr_l);
+                if (lane == l) cnt = m_l;
+            }
+            p.counts[(size_t)chunk * p.nq_pad + q] = active ? cnt : 0;
+        }
+    }
+
+    // ----- teardown: every async op has been consumed by now (the epilogue waited on the last commit)
+    tc_fence_before();
+    if (CG > 1) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, 512);
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr) return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// rows x cols 16-bit matrix, row stride ld elements; box = 64 cols x box_rows, 128B swizzle, OOB -> 0
+static int encode_2d(CUtensorMap* m, const void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = (dtype == VQ_DTYPE_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+template <int CG>
+static int launch_cg(const CUtensorMap& tq, const CUtensorMap& tx, const TcParams& p, int n_clusters, cudaStream_t stream) {
+    using C = Cfg<CG>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e != cudaSuccess) return -(int)e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * CG));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_topk_kernel<CG>, tq, tx, p);
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+}  // namespace tc
+
+// Plans the (m_tile, chunk) decomposition for nq queries over n_rows corpus rows on n_sms SMs.
+void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan) {
+    int cg = force_cg;
+    if (cg != 1 && cg != 2) cg = (nq > tc::BLOCK_Q) ? 2 : 1;
+    const int n_clusters_max = n_sms / cg;
+    const int m_tiles = (nq + tc::BLOCK_Q * cg - 1) / (tc::BLOCK_Q * cg);
+    const int n_tiles = (int)((n_rows + tc::BLOCK_N - 1) / tc::BLOCK_N);
+    // smallest chunk count whose (m_tile, chunk) items spread evenly over the clusters
+    int best_c = 1;
+    double best_eff = 0.0;
+    const int c_max = n_tiles < 4 * n_clusters_max ? (n_tiles > 0 ? n_tiles : 1) : 4 * n_clusters_max;
+    for (int c = 1; c <= c_max; c++) {
+        const int tpc = (n_tiles + c - 1) / c;
+        const int c_eff = (n_tiles + tpc - 1) / tpc;
+        const long long items = (long long)m_tiles * c_eff;
+        const long long rounds = (items + n_clusters_max - 1) / n_clusters_max;
+        // cost model: rounds * tiles_per_chunk tile-times for the slowest cluster
+        const double eff = (double)m_tiles * n_tiles / ((double)rounds * tpc * n_clusters_max);
+        if (eff > best_eff + 0.02) { best_eff = eff; best_c = c; }
+        if (best_eff > 0.97) break;
+    }
+    const int tpc = n_tiles > 0 ? (n_tiles + best_c - 1) / best_c : 1;
+    plan->cg = cg;
+    plan->m_tiles = m_tiles;
+    plan->n_tiles = n_tiles;
+    plan->tiles_per_chunk = tpc;
+    plan->n_chunks = n_tiles > 0 ? (n_tiles + tpc - 1) / tpc : 1;
+    plan->nq_pad = m_tiles * tc::BLOCK_Q * cg;
+    const long long items = (long long)plan->m_tiles * plan->n_chunks;
+    plan->n_clusters = (int)(items < n_clusters_max ? items : n_clusters_max);
+    if (plan->n_clusters < 1) plan->n_clusters = 1;
+}
+
+// q16: [nq, ld_q] 16-bit queries (device); x16: [n_rows, ld_x] 16-bit corpus (device)
+int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
+                   const TcPlan& plan, uint64_t* lists, int* counts, cudaStream_t stream) {
+    if (k < 1 || k > VQ_KMAX) return -2;
+    if (n_rows <= 0 || nq <= 0) return 0;
+    CUtensorMap tq, tx;
+    int rc = tc::encode_2d(&tq, q16, dtype, (uint64_t)nq, (uint64_t)d, (uint64_t)ld_q, tc::BLOCK_Q);
+    if (rc) return rc;
+    rc = tc::encode_2d(&tx, x16, dtype, (uint64_t)n_rows, (uint64_t)d, (uint64_t)ld_x, (uint32_t)(tc::BLOCK_N / plan.cg));
+    if (rc) return rc;
+    TcParams p;
+    p.lists = lists;
+    p.counts = counts;
+    p.n_rows = n_rows;
+    p.nq = nq;
+    p.nq_pad = plan.nq_pad;
+    p.k = k;
+    p.num_kb = (d + tc::BLOCK_K - 1) / tc::BLOCK_K;
+    p.m_tiles = plan.m_tiles;
+    p.n_tiles = plan.n_tiles;
+    p.n_chunks = plan.n_chunks;
+    p.tiles_per_chunk = plan.tiles_per_chunk;
+    // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format bf16 = 1 / f16 = 0 (bits 7-9, 10-12), both K-major
+    const uint32_t fmt = (dtype == VQ_DTYPE_BF16) ? 1u : 0u;
+    p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10);
+    return plan.cg == 2 ? tc::launch_cg<2>(tq, tx, p, plan.n_clusters, stream) : tc::launch_cg<1>(tq, tx, p, plan.n_clusters, stream);
+}
+
+}  // namespace vq
