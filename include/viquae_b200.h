@@ -68,6 +68,12 @@ int vq_index_dtype(const vq_index* idx);
 int vq_index_set_id_offset(vq_index* idx, int64_t id_offset);
 int vq_index_set_variant(vq_index* idx, int variant);
 
+/* Measurement support (bench.py): when enabled, every vq_index_search records a CUDA event pair around
+ * its dominant kernel (the contraction + fused top-k) on the launch stream; read_timing waits for the
+ * recorded pairs, returns their summed duration and count, and resets.  At most 256 searches are kept. */
+int vq_index_set_timing(vq_index* idx, int enable);
+int vq_index_read_timing(vq_index* idx, double* total_ms, int* n_launches);
+
 /* faiss Index::reconstruct_n — copy rows [start, start+n) out as dst_dtype, [n, d] row-major,
  * host or device destination.  Used by save/load (meerqat/ir/search.py:234-248). */
 int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* dst, int dst_dtype, void* stream);

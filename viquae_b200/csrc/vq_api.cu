@@ -24,6 +24,8 @@ static int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(VQ_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+#define VQ_TIMING_SLOTS 256
+
 struct vq_index {
     int d, dtype, device, ld, n_sms, variant;
     uint64_t capacity, ntotal;
@@ -32,6 +34,10 @@ struct vq_index {
     // engine-owned buffers of the host-buffer entry point
     void* hws;
     size_t hws_bytes;
+    // measurement support: CUDA events around the dominant kernel of each search
+    int timing;
+    int n_timed;
+    cudaEvent_t ev0[VQ_TIMING_SLOTS], ev1[VQ_TIMING_SLOTS];
 };
 
 static size_t esize(int dtype) { return dtype == VQ_F32 ? 4 : 2; }
@@ -75,6 +81,8 @@ int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capac
     idx->data = nullptr;
     idx->hws = nullptr;
     idx->hws_bytes = 0;
+    idx->timing = 0;
+    idx->n_timed = 0;
     if (capacity) {
         cudaError_t e = cudaMalloc(&idx->data, capacity * idx->ld * esize(dtype));
         if (e != cudaSuccess) {
@@ -92,6 +100,11 @@ void vq_index_destroy(vq_index* idx) {
     cudaSetDevice(idx->device);
     if (idx->data) cudaFree(idx->data);
     if (idx->hws) cudaFree(idx->hws);
+    if (idx->timing)
+        for (int i = 0; i < VQ_TIMING_SLOTS; i++) {
+            cudaEventDestroy(idx->ev0[i]);
+            cudaEventDestroy(idx->ev1[i]);
+        }
     delete idx;
 }
 
@@ -107,6 +120,42 @@ int vq_index_set_id_offset(vq_index* idx, int64_t off) {
 int vq_index_set_variant(vq_index* idx, int variant) {
     if (!idx || variant < 0 || variant > 3) return fail(VQ_ERR_INVALID, "vq_index_set_variant: bad variant %d", variant);
     idx->variant = variant;
+    return VQ_OK;
+}
+
+int vq_index_set_timing(vq_index* idx, int enable) {
+    if (!idx) return fail(VQ_ERR_INVALID, "null index");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    if (enable && !idx->timing) {
+        for (int i = 0; i < VQ_TIMING_SLOTS; i++) {
+            CUDA_TRY(cudaEventCreate(&idx->ev0[i]));
+            CUDA_TRY(cudaEventCreate(&idx->ev1[i]));
+        }
+        idx->timing = 1;
+    }
+    if (!enable && idx->timing) {
+        for (int i = 0; i < VQ_TIMING_SLOTS; i++) {
+            cudaEventDestroy(idx->ev0[i]);
+            cudaEventDestroy(idx->ev1[i]);
+        }
+        idx->timing = 0;
+    }
+    idx->n_timed = 0;
+    return VQ_OK;
+}
+
+int vq_index_read_timing(vq_index* idx, double* total_ms, int* n_launches) {
+    if (!idx || !total_ms || !n_launches) return fail(VQ_ERR_INVALID, "vq_index_read_timing: null pointer");
+    double tot = 0.0;
+    for (int i = 0; i < idx->n_timed; i++) {
+        CUDA_TRY(cudaEventSynchronize(idx->ev1[i]));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, idx->ev0[i], idx->ev1[i]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *n_launches = idx->n_timed;
+    idx->n_timed = 0;
     return VQ_OK;
 }
 
@@ -280,6 +329,8 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     int* counts = (int*)(ws + sp.off_counts);
     int rc = vq::prep_rows_launch(q, q_dtype, idx->d, qprep, idx->dtype, idx->ld, nq, idx->d, l2norm_q, s);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
+    const bool timed = idx->timing && idx->n_timed < VQ_TIMING_SLOTS && idx->ntotal;
+    if (timed) CUDA_TRY(cudaEventRecord(idx->ev0[idx->n_timed], s));
     if (idx->ntotal == 0) {
         CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)sp.n_chunks * sp.nq_pad * sizeof(int), s));
     } else if (sp.kind == 0) {
@@ -293,6 +344,10 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
                                     counts, s);
     }
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: kernel launch failed (%d: %s)", rc, rc < 0 && rc > -1000 ? cudaGetErrorString((cudaError_t)(-rc)) : "driver");
+    if (timed) {
+        CUDA_TRY(cudaEventRecord(idx->ev1[idx->n_timed], s));
+        idx->n_timed++;
+    }
     rc = vq::merge_lists_launch(lists, counts, sp.n_chunks, sp.nq_pad, nq, k, idx->id_offset, out_scores, (long long*)out_ids, s);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: merge launch failed (%d)", rc);
     return VQ_OK;

@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, TcParams p) {
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (128B swizzle) computed in the shared window so both CTAs of a pair get the same offsets
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -239,6 +240,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the leader CTA) =====================
         if (leader && lane == 0) {
@@ -270,6 +272,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 }
             }
         }
+        __syncwarp();
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> registers -> threshold filter -> candidate lists =====================
         const int ew = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quarter this warp may read
