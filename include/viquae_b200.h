@@ -73,6 +73,8 @@ int vq_index_set_variant(vq_index* idx, int variant);
  * recorded pairs, returns their summed duration and count, and resets.  At most 256 searches are kept. */
 int vq_index_set_timing(vq_index* idx, int enable);
 int vq_index_read_timing(vq_index* idx, double* total_ms, int* n_launches);
+/* Cumulative number of CUDA kernels vq_index_search has launched on this index (bench.py: gpu_launches). */
+uint64_t vq_index_launch_count(const vq_index* idx);
 
 /* faiss Index::reconstruct_n — copy rows [start, start+n) out as dst_dtype, [n, d] row-major,
  * host or device destination.  Used by save/load (meerqat/ir/search.py:234-248). */

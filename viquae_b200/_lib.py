@@ -30,6 +30,7 @@ SIGNATURES = {
     "vq_index_set_variant": (c_int, [c_void_p, c_int]),
     "vq_index_set_timing": (c_int, [c_void_p, c_int]),
     "vq_index_read_timing": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int)]),
+    "vq_index_launch_count": (c_uint64, [c_void_p]),
     "vq_index_copy_rows": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p, c_int, c_void_p]),
     "vq_index_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "vq_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

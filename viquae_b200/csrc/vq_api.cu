@@ -37,6 +37,7 @@ struct vq_index {
     // measurement support: CUDA events around the dominant kernel of each search
     int timing;
     int n_timed;
+    uint64_t launches;  // kernels launched by vq_index_search so far
     cudaEvent_t ev0[VQ_TIMING_SLOTS], ev1[VQ_TIMING_SLOTS];
 };
 
@@ -83,6 +84,7 @@ int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capac
     idx->hws_bytes = 0;
     idx->timing = 0;
     idx->n_timed = 0;
+    idx->launches = 0;
     if (capacity) {
         cudaError_t e = cudaMalloc(&idx->data, capacity * idx->ld * esize(dtype));
         if (e != cudaSuccess) {
@@ -109,6 +111,7 @@ void vq_index_destroy(vq_index* idx) {
 }
 
 uint64_t vq_index_ntotal(const vq_index* idx) { return idx ? idx->ntotal : 0; }
+uint64_t vq_index_launch_count(const vq_index* idx) { return idx ? idx->launches : 0; }
 int vq_index_dim(const vq_index* idx) { return idx ? idx->d : 0; }
 int vq_index_dtype(const vq_index* idx) { return idx ? idx->dtype : -1; }
 
@@ -262,45 +265,78 @@ int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* ds
 }
 
 // ---- variant choice + workspace carving shared by workspace_bytes() and search()
+#define VQ_MAX_PASSES 6
 struct SearchPlan {
     int kind;  // 0 = fp32 SIMT, 1 = tensor core, 2 = stream
-    vq::TcPlan tc;
+    // tensor-core path: corpus tiles [tile_b[p], tile_b[p+1]) are searched by pass p with thresholds primed
+    // from all earlier passes (see make_plan)
+    int n_passes;
+    int tile_b[VQ_MAX_PASSES + 1];
+    vq::TcPlan tc[VQ_MAX_PASSES];
     vq::F32Plan f32;
     vq::StreamPlan st;
-    int n_chunks, nq_pad;
-    size_t off_q, off_lists, off_counts, total;
+    int pass_sets;  // largest number of candidate-list sets any pass writes (set 0 is the running merge)
+    int nq_pad;
+    size_t off_q, off_lists, off_counts, off_thr, total;
 };
 
 static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     const long long n = (long long)idx->ntotal;
+    sp->n_passes = 1;
     if (idx->dtype == VQ_F32) {
         sp->kind = 0;
         vq::f32_plan(nq, n, idx->n_sms, &sp->f32);
-        sp->n_chunks = sp->f32.n_chunks;
+        sp->pass_sets = sp->f32.n_chunks;
         sp->nq_pad = sp->f32.nq_pad;
     } else {
         int variant = idx->variant;
-        if (variant == VQ_VARIANT_AUTO) variant = (nq <= 32) ? VQ_VARIANT_STREAM : (nq <= 128 ? VQ_VARIANT_TC_CG1 : VQ_VARIANT_TC_CG2);
+        if (variant == VQ_VARIANT_AUTO) variant = (nq <= 128) ? VQ_VARIANT_TC_CG1 : VQ_VARIANT_TC_CG2;
         if (variant == VQ_VARIANT_STREAM && nq > 32) variant = VQ_VARIANT_TC_CG1;
         if (variant == VQ_VARIANT_STREAM) {
             sp->kind = 2;
             vq::stream_plan(nq, n, idx->n_sms, &sp->st);
-            sp->n_chunks = sp->st.n_chunks;
+            sp->pass_sets = sp->st.n_chunks;
             sp->nq_pad = sp->st.nq_pad;
         } else {
             sp->kind = 1;
-            vq::tc_plan(nq, n, idx->n_sms, variant == VQ_VARIANT_TC_CG2 ? 2 : 1, &sp->tc);
-            sp->n_chunks = sp->tc.n_chunks;
-            sp->nq_pad = sp->tc.nq_pad;
+            const int cg = variant == VQ_VARIANT_TC_CG2 ? 2 : 1;
+            // Threshold priming.  A query's k-th best score over ANY subset of the corpus is a lower bound of its
+            // final k-th best score, so the corpus is searched in passes of geometrically growing size (x16): the
+            // first pass is one tile per work item (nothing to prune yet), every later pass starts from the k-th
+            // score of everything before it and therefore rejects almost every 32-score block with a single
+            // compare; it appends only ~16k candidates per query.  Rows of later passes have higher ids, so a
+            // score equal to the threshold loses the tie and the strict compare stays exact.
+            const int n_tiles = (int)((n + 255) / 256);
+            const int m_tiles = (nq + 128 * cg - 1) / (128 * cg);
+            int first = (idx->n_sms / cg) / m_tiles;
+            if (first < 1) first = 1;
+            if (first > 28) first = 28;  // every row of the first pass becomes a candidate: keep its merge one 8192-key sort
+            int np = 0;
+            sp->tile_b[0] = 0;
+            long long b = first;
+            while (np < VQ_MAX_PASSES - 1 && b * 4 < n_tiles) {
+                sp->tile_b[++np] = (int)b;
+                b *= 16;
+            }
+            sp->tile_b[++np] = n_tiles;
+            sp->n_passes = np;
+            sp->pass_sets = 0;
+            for (int p = 0; p < np; p++) {
+                vq::tc_plan(nq, (long long)(sp->tile_b[p + 1] - sp->tile_b[p]) * 256, idx->n_sms, cg, &sp->tc[p]);
+                if (sp->tc[p].list_sets > sp->pass_sets) sp->pass_sets = sp->tc[p].list_sets;
+            }
+            sp->nq_pad = sp->tc[0].nq_pad;
         }
     }
     size_t off = 0;
     sp->off_q = off;
     off += align256((size_t)(nq > sp->nq_pad ? nq : sp->nq_pad) * idx->ld * esize(idx->dtype));
     sp->off_lists = off;
-    off += align256((size_t)sp->n_chunks * sp->nq_pad * VQ_CAP * sizeof(uint64_t));
+    off += align256((size_t)(1 + sp->pass_sets) * sp->nq_pad * VQ_CAP * sizeof(uint64_t));
     sp->off_counts = off;
-    off += align256((size_t)sp->n_chunks * sp->nq_pad * sizeof(int));
+    off += align256((size_t)(1 + sp->pass_sets) * sp->nq_pad * sizeof(int));
+    sp->off_thr = off;
+    off += align256((size_t)sp->nq_pad * sizeof(float));
     sp->total = off;
 }
 
@@ -327,29 +363,52 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     void* qprep = ws + sp.off_q;
     uint64_t* lists = (uint64_t*)(ws + sp.off_lists);
     int* counts = (int*)(ws + sp.off_counts);
+    float* thr = (float*)(ws + sp.off_thr);
     int rc = vq::prep_rows_launch(q, q_dtype, idx->d, qprep, idx->dtype, idx->ld, nq, idx->d, l2norm_q, s);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
+    idx->launches += 1;
+    // rows [nq, nq_pad) of the prepared query matrix are real zero rows, so the tensor-core path never
+    // depends on TMA out-of-bounds fill for the query operand
+    if (sp.nq_pad > nq)
+        CUDA_TRY(cudaMemsetAsync((uint8_t*)qprep + (size_t)nq * idx->ld * esize(idx->dtype), 0,
+                                 (size_t)(sp.nq_pad - nq) * idx->ld * esize(idx->dtype), s));
     const bool timed = idx->timing && idx->n_timed < VQ_TIMING_SLOTS && idx->ntotal;
     if (timed) CUDA_TRY(cudaEventRecord(idx->ev0[idx->n_timed], s));
-    if (idx->ntotal == 0) {
-        CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)sp.n_chunks * sp.nq_pad * sizeof(int), s));
-    } else if (sp.kind == 0) {
-        rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, (long long)idx->ntotal, idx->ld, idx->d, k,
-                                 sp.f32, lists, counts, s);
+    const long long ntot = (long long)idx->ntotal;
+    if (ntot == 0) {
+        CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(1 + sp.pass_sets) * sp.nq_pad * sizeof(int), s));
+        rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, idx->id_offset, nullptr, out_scores, (long long*)out_ids, 512, s);
+        idx->launches += 1;
     } else if (sp.kind == 1) {
-        rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, (long long)idx->ntotal, idx->ld, idx->d, idx->dtype, k, sp.tc, lists,
-                                counts, s);
+        for (int p = 0; p < sp.n_passes && !rc; p++) {
+            const bool last = p == sp.n_passes - 1;
+            vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, p ? thr : nullptr, 1};
+            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 256;
+            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, rows_end, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, s);
+            // first pass: every list holds at most min(CAP, its rows); primed passes add ~16k candidates per query
+            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : 4096;
+            if (!rc)
+                rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.tc[p].list_sets, sp.nq_pad, nq, k, idx->id_offset, last ? nullptr : thr,
+                                            last ? out_scores : nullptr, last ? (long long*)out_ids : nullptr, expected, s);
+            idx->launches += 2;
+        }
     } else {
-        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, (long long)idx->ntotal, idx->ld, idx->d, idx->dtype, k, sp.st, lists,
-                                    counts, s);
+        if (sp.kind == 0)
+            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, ntot, idx->ld, idx->d, k, sp.f32,
+                                     lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
+        else
+            rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.st,
+                                        lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
+        if (!rc)
+            rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, idx->id_offset, nullptr, out_scores,
+                                        (long long*)out_ids, sp.pass_sets * k, s);
+        idx->launches += 2;
     }
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: kernel launch failed (%d: %s)", rc, rc < 0 && rc > -1000 ? cudaGetErrorString((cudaError_t)(-rc)) : "driver");
     if (timed) {
         CUDA_TRY(cudaEventRecord(idx->ev1[idx->n_timed], s));
         idx->n_timed++;
     }
-    rc = vq::merge_lists_launch(lists, counts, sp.n_chunks, sp.nq_pad, nq, k, idx->id_offset, out_scores, (long long*)out_ids, s);
-    if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: merge launch failed (%d)", rc);
     return VQ_OK;
 }
 

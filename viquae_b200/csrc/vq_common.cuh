@@ -5,7 +5,7 @@
 // so that "larger key" == "ranks earlier": higher score first, then LOWER row id (the tie rule the
 // oracle fixes; FAISS IndexFlat leaves it open).  Rows are shard-local uint32 (< 2^32 per GPU).
 //
-// Candidate lists.  Each (work item, query) owns a list of VQ_CAP keys in the caller-provided
+// Candidate lists.  Each (work item, query) owns a list of VQ_CAP (score, row) pairs in the caller-provided
 // workspace (HBM, L2-resident in practice).  Kernels append every score that beats the running
 // threshold; when a list could overflow, one warp sorts it (bitonic, registers + shuffles), keeps
 // the best k and raises the threshold to the k-th score.  Nothing above the true k-th score of
@@ -38,37 +38,50 @@ __device__ __forceinline__ uint64_t make_key(float s, uint32_t row) {
 __device__ __forceinline__ float key_score(uint64_t k) { return ord2f((uint32_t)(k >> 32)); }
 __device__ __forceinline__ uint32_t key_row(uint64_t k) { return ~(uint32_t)k; }
 
+// Candidate lists hold RAW pairs (row << 32 | float bits of the score): pushing costs one 8-byte store
+// on the hot path; the order-preserving key is built when a list is pruned or merged.
+__device__ __forceinline__ uint64_t pack_raw(float s, uint32_t row) { return ((uint64_t)row << 32) | (uint64_t)__float_as_uint(s); }
+__device__ __forceinline__ uint64_t raw_to_key(uint64_t raw) { return make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32)); }
+__device__ __forceinline__ uint64_t key_to_raw(uint64_t key) { return pack_raw(key_score(key), key_row(key)); }
+
 __device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
 // Bitonic sort, descending, of 32*E keys held E per lane; element e = r*32 + lane.
+// The network is kept ROLLED (runtime stage size s and cross-lane stride j) so that the code stays a
+// few hundred instructions and can be inlined wherever a list is pruned; only the in-register
+// exchanges (stride >= 32, compile-time register distance) are unrolled.
+template <int E, int RJ>
+__device__ __forceinline__ void bitonic_inreg_stage(uint64_t (&key)[E], int s) {
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        if ((r & RJ) == 0) {
+            const bool desc = (((r * 32) & s) == 0);
+            const uint64_t a = key[r], b = key[r | RJ];
+            const bool sw = desc ? (a < b) : (a > b);
+            key[r] = sw ? b : a;
+            key[r | RJ] = sw ? a : b;
+        }
+    }
+}
+
 template <int E>
 __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&key)[E], int lane) {
-#pragma unroll
+    static_assert(E == 8, "warp_bitonic_sort_desc is written for 256 keys per warp");
+#pragma unroll 1
     for (int s = 2; s <= 32 * E; s <<= 1) {
+        if (s >= 256) bitonic_inreg_stage<E, 4>(key, s);
+        if (s >= 128) bitonic_inreg_stage<E, 2>(key, s);
+        if (s >= 64) bitonic_inreg_stage<E, 1>(key, s);
+#pragma unroll 1
+        for (int j = (s >> 1) < 16 ? (s >> 1) : 16; j > 0; j >>= 1) {
+            const bool lower = (lane & j) == 0;
 #pragma unroll
-        for (int j = s >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int rj = j >> 5;
-#pragma unroll
-                for (int r = 0; r < E; r++) {
-                    if ((r & rj) == 0) {
-                        const bool desc = (((r * 32) & s) == 0);
-                        uint64_t a = key[r], b = key[r | rj];
-                        const bool sw = desc ? (a < b) : (a > b);
-                        key[r] = sw ? b : a;
-                        key[r | rj] = sw ? a : b;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < E; r++) {
-                    const int e = r * 32 + lane;
-                    const uint64_t other = __shfl_xor_sync(VQ_FULL_MASK, key[r], j);
-                    const bool lower = (lane & j) == 0;
-                    const bool desc = ((e & s) == 0);
-                    key[r] = (lower == desc) ? umax64(key[r], other) : umin64(key[r], other);
-                }
+            for (int r = 0; r < E; r++) {
+                const int e = r * 32 + lane;
+                const uint64_t other = __shfl_xor_sync(VQ_FULL_MASK, key[r], j);
+                const bool desc = ((e & s) == 0);
+                key[r] = (lower == desc) ? umax64(key[r], other) : umin64(key[r], other);
             }
         }
     }
@@ -82,14 +95,14 @@ __device__ __forceinline__ int warp_prune_list(uint64_t* list, int n, int k, int
 #pragma unroll
     for (int r = 0; r < VQ_CAP / 32; r++) {
         const int e = r * 32 + lane;
-        key[r] = (e < n) ? __ldcg(reinterpret_cast<const unsigned long long*>(list) + e) : 0ull;
+        key[r] = (e < n) ? raw_to_key(__ldcg(reinterpret_cast<const unsigned long long*>(list) + e)) : 0ull;
     }
     warp_bitonic_sort_desc<VQ_CAP / 32>(key, lane);
     const int m = n < k ? n : k;
 #pragma unroll
     for (int r = 0; r < VQ_KMAX / 32; r++) {
         const int e = r * 32 + lane;
-        if (e < m) __stcg(reinterpret_cast<unsigned long long*>(list) + e, (unsigned long long)key[r]);
+        if (e < m) __stcg(reinterpret_cast<unsigned long long*>(list) + e, (unsigned long long)key_to_raw(key[r]));
     }
     uint64_t kth = 0;
     const int rk = (k - 1) >> 5, lk = (k - 1) & 31;

@@ -126,7 +126,7 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
                     const float s = acc[i][j];
                     if (xr < n_rows && s > thr) {
                         const int pos = atomicAdd(&cnt_s[r], 1);
-                        __stcg(list + pos, (unsigned long long)make_key(s, (uint32_t)xr));
+                        __stcg(list + pos, (unsigned long long)pack_raw(s, (uint32_t)xr));
                     }
                 }
             }
@@ -163,7 +163,8 @@ void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan) {
     const int n_tiles = (int)((n_rows + f32::BN - 1) / f32::BN);
     int best_c = 1;
     double best_eff = 0.0;
-    const int c_max = n_tiles < 4 * max_ctas ? (n_tiles > 0 ? n_tiles : 1) : 4 * max_ctas;
+    int c_max = n_tiles < 4 * max_ctas ? (n_tiles > 0 ? n_tiles : 1) : 4 * max_ctas;
+    if (c_max > 1000) c_max = 1000;  // the merge kernel takes at most 1023 list sets
     for (int c = 1; c <= c_max; c++) {
         const int tpc = (n_tiles + c - 1) / c;
         const int c_eff = (n_tiles + tpc - 1) / tpc;

@@ -20,21 +20,32 @@ struct TcPlan {
     int cg;               // CTAs per cluster (1 or 2)
     int m_tiles;          // query tiles of 128*cg
     int n_tiles;          // corpus tiles of 256 rows
-    int n_chunks;         // corpus slabs; work item = (m_tile, chunk)
+    int n_chunks;         // residue classes G of corpus tiles; work item = (m_tile, g), tiles g, g+G, ...
     int tiles_per_chunk;
+    int list_sets;        // candidate-list sets written: n_chunks * column halves
     int nq_pad;           // m_tiles * 128 * cg
     int n_clusters;       // persistent clusters launched
 };
 struct TcParams {
-    uint64_t* lists;      // [n_chunks][nq_pad][VQ_CAP] candidate keys
-    int* counts;          // [n_chunks][nq_pad]
+    uint64_t* lists;      // [list_sets][nq_pad][VQ_CAP] candidate (score, row) pairs
+    int* counts;          // [list_sets][nq_pad]
     long long n_rows;
     int nq, nq_pad, k, num_kb, m_tiles, n_tiles, n_chunks, tiles_per_chunk;
+    int tile_begin;       // first corpus tile of this pass (n_tiles is the absolute end)
+    int list_set_base;    // first candidate-list set this pass writes
+    const float* init_thr;  // optional primed per-query thresholds: init_thr[q * init_thr_stride]
+    int init_thr_stride;
     uint32_t idesc_base;
+};
+// one pass over corpus tiles [tile_begin, tile_end): plan must come from tc_plan(nq, (tile_end - tile_begin) * 256 rows)
+struct TcPass {
+    int tile_begin, tile_end, list_set_base;
+    const float* init_thr;
+    int init_thr_stride;
 };
 void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan);
 int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
-                   const TcPlan& plan, uint64_t* lists, int* counts, cudaStream_t stream);
+                   const TcPlan& plan, const TcPass& pass, uint64_t* lists, int* counts, cudaStream_t stream);
 
 // ---- K1: fp32 exact SIMT contraction + fused top-k (vq_fp32.cu)
 struct F32Plan {
@@ -54,9 +65,12 @@ int stream_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long 
                        const StreamPlan& plan, uint64_t* lists, int* counts, cudaStream_t stream);
 
 // ---- K4: merges (vq_merge.cu)
-// candidate-key lists [n_chunks][nq_pad][VQ_CAP] (+counts) -> final [nq][k] scores (f32) / ids (i64, + id_offset)
-int merge_lists_launch(const uint64_t* lists, const int* counts, int n_chunks, int nq_pad, int nq, int k, long long id_offset,
-                       float* out_scores, long long* out_ids, cudaStream_t stream);
+// Merge step of one pass.  Candidate lists are [set][nq_pad][VQ_CAP] raw pairs + counts[set][nq_pad]; set 0 is
+// the RUNNING merged top-k of all passes so far.  Gathers set 0 (if use_set0) + sets [set_begin, set_begin+n_sets),
+// keeps the best k in set 0, writes every query's k-th score to thr_out (may be null) and, if out_scores is
+// given, the final [nq][k] scores (f32) / ids (i64, + id_offset).  expected_total sizes the shared-memory sort.
+int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
+                       float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream);
 // per-shard results [n_lists][nq][k_in] (scores f32, ids i64; id < 0 = padding) -> [nq][k_out]
 int merge_topk_launch(const float* scores, const long long* ids, int n_lists, int nq, int k_in, int k_out,
                       float* out_scores, long long* out_ids, cudaStream_t stream);

@@ -120,7 +120,7 @@ stream_topk_kernel(const uint16_t* __restrict__ Q, int nq, int ld_q, const uint1
                 if (valid && s > thr[nt][i & 1]) {
                     const int pos = atomicAdd(&cnt_s[qi], 1);
                     __stcg(reinterpret_cast<unsigned long long*>(cta_lists + (size_t)qi * VQ_CAP) + pos,
-                           (unsigned long long)make_key(s, (uint32_t)((i < 2) ? ra : rb)));
+                           (unsigned long long)pack_raw(s, (uint32_t)((i < 2) ? ra : rb)));
                 }
             }
         }

@@ -14,8 +14,14 @@
 // tcgen05.mma.cta_group::2 with UMMA 256x256x16: each CTA holds 128 queries and HALF of the corpus
 // tile, halving the L2->SM corpus traffic per query row.
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM
-// allocator, warp 3 idle, warps 4..7 epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM
+// allocator, warp 3 idle, warps 4..11 epilogue (TMEM lane quarter = warp % 4, column half =
+// (warp - 4) / 4).  The epilogue is the critical path next to the MMA: its inner loop is branch-free
+// (predicated 8-byte stores of raw (score, row) pairs through inline PTX).
+//
+// Work decomposition: item = (query tile, residue class g): the item's corpus tiles are
+// g, g + G, g + 2G, ... so that at any moment all clusters work inside a window of ~G tiles and the
+// clusters of different query tiles hit the same corpus tiles in L2.
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
@@ -29,8 +35,11 @@ constexpr int BLOCK_N = 256;   // corpus rows per tile (UMMA_N, TMEM columns)
 constexpr int BLOCK_K = 64;    // 64 x 2 B = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int ACC_STAGES = 2;  // 2 x 256 columns = all 512 TMEM columns
-constexpr int THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter: each takes half of the tile's columns
+constexpr int EPI_HALVES = EPI_WARPS / 4;
+constexpr int EPI_COLS = BLOCK_N / EPI_HALVES;  // 128 columns per epilogue warp
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;  // 384
 constexpr uint32_t A_STAGE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KB
 
 template <int CG> struct Cfg {
@@ -156,6 +165,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// if (s > thr) { list[cnt++] = ((rbase + J) << 32 | bits(s)); }  — predicated, no branch
+template <int J>
+__device__ __forceinline__ void push_if_gt_imm(unsigned long long* list, uint32_t& cnt, uint32_t s_bits, float thr, uint32_t rbase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 a;\n"
+        ".reg .b32 r;\n"
+        "setp.gt.f32 p, %2, %3;\n"
+        "mad.wide.u32 a, %0, 8, %1;\n"   // temporaries are written unconditionally: a predicated write would
+        "add.u32 r, %5, %6;\n"           // make ptxas keep their old values alive across the whole loop
+        "@p st.global.cg.v2.b32 [a], {%4, r};\n"
+        "@p add.u32 %0, %0, 1;\n"
+        "}\n"
+        : "+r"(cnt)
+        : "l"(list), "f"(__uint_as_float(s_bits)), "f"(thr), "r"(s_bits), "r"(rbase), "n"(J)
+        : "memory");
+}
+template <int J0, int J1>
+__device__ __forceinline__ void push_block(unsigned long long* list, uint32_t& cnt, const uint32_t (&v)[32], float thr, uint32_t rbase, int lim) {
+    if constexpr (J0 < J1) {
+        push_if_gt_imm<J0>(list, cnt, v[J0], (J0 < lim) ? thr : INFINITY, rbase);
+        push_block<J0 + 1, J1>(list, cnt, v, thr, rbase, lim);
+    }
+}
+
 // K-major, 128-byte-swizzled operand tile: 8-row groups are 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -202,7 +237,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         for (int i = 0; i < ACC_STAGES; i++) {
             mbar_init(&tmem_full_bar[i], 1);        // one tcgen05.commit
-            mbar_init(&tmem_empty_bar[i], CG * 4);  // one arrival per epilogue warp of each CTA
+            mbar_init(&tmem_empty_bar[i], CG * EPI_WARPS);  // one arrival per epilogue warp of each CTA
         }
         fence_barrier_init();
     } else if (warp == 2) {
@@ -223,9 +258,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int m_tile = item % p.m_tiles, chunk = item / p.m_tiles;
                 const int q_row0 = (m_tile * CG + (int)rank) * BLOCK_Q;
-                const int t0 = chunk * p.tiles_per_chunk;
-                const int t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
-                for (int t = t0; t < t1; t++) {
+                for (int t = p.tile_begin + chunk; t < p.n_tiles; t += p.n_chunks) {
                     const int x_row0 = t * BLOCK_N + (int)rank * C::LOAD_N;
                     for (int kb = 0; kb < num_kb; kb++) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -248,9 +281,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             uint32_t stage = 0, phase = 0, iter = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int chunk = item / p.m_tiles;
-                const int t0 = chunk * p.tiles_per_chunk;
-                const int t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
-                for (int t = t0; t < t1; t++, iter++) {
+                for (int t = p.tile_begin + chunk; t < p.n_tiles; t += p.n_chunks, iter++) {
                     const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                     mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
                     tc_fence_after();
@@ -275,7 +306,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         __syncwarp();
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> registers -> threshold filter -> candidate lists =====================
-        const int ew = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quarter this warp may read
+        const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: the TMEM lane quarter this warp may read
+        const int half = (warp - EPI_WARP0) >> 2;  // which EPI_COLS-wide slice of the tile's columns
         const uint32_t lane_field = (uint32_t)(ew * 32) << 16;
         const int k = p.k;
         uint32_t iter = 0;
@@ -283,72 +315,61 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const int m_tile = item % p.m_tiles, chunk = item / p.m_tiles;
             const int q = (m_tile * CG + (int)rank) * BLOCK_Q + ew * 32 + lane;  // this thread's query
             const int q0_warp = q - lane;
-            uint64_t* warp_lists = p.lists + ((size_t)chunk * p.nq_pad + q0_warp) * VQ_CAP;
-            unsigned long long* my_list = reinterpret_cast<unsigned long long*>(warp_lists + (size_t)lane * VQ_CAP);
+            const size_t list_set = (size_t)p.list_set_base + (size_t)chunk * EPI_HALVES + half;  // candidate lists are per (residue class, column half)
+            uint64_t* warp_lists = p.lists + (list_set * p.nq_pad + q0_warp) * VQ_CAP;
+            unsigned long long* const my_list = reinterpret_cast<unsigned long long*>(warp_lists + (size_t)lane * VQ_CAP);
+            uint32_t cnt = 0;
             const bool active = q < p.nq;
-            int cnt = 0;
-            float thr = active ? -FLT_MAX : INFINITY;
-            const int t0 = chunk * p.tiles_per_chunk;
-            const int t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
-            for (int t = t0; t < t1; t++, iter++) {
+            // primed threshold: the k-th best score of an already-searched sample of the corpus (rows below
+            // tile_begin * 256), a valid lower bound of the final k-th score; ties lose (higher row id)
+            float thr = active ? (p.init_thr ? p.init_thr[(size_t)q * p.init_thr_stride] : -FLT_MAX) : INFINITY;
+            for (int t = p.tile_begin + chunk; t < p.n_tiles; t += p.n_chunks, iter++) {
                 const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                 mbar_wait(&tmem_full_bar[as], aphase);
                 tc_fence_after();
-                const uint32_t row0 = (uint32_t)t * BLOCK_N;
-                const int n_valid = (int)min((long long)BLOCK_N, p.n_rows - (long long)row0);
+                const uint32_t row0 = (uint32_t)t * BLOCK_N + half * EPI_COLS;
+                const int n_valid = (int)min((long long)EPI_COLS, p.n_rows - (long long)row0);  // may be <= 0
+                const uint32_t tcol0 = tmem_base + lane_field + as * BLOCK_N + half * EPI_COLS;
 #pragma unroll 1
-                for (int cb = 0; cb < BLOCK_N / 32; cb++) {
-                    // make room: a 32-column block can append at most 32 keys to a list
+                for (int cb = 0; cb < EPI_COLS / 32; cb++) {
+                    // make room first (nothing else is live across the call): a block appends at most 32 pairs
                     unsigned need = __ballot_sync(VQ_FULL_MASK, cnt > VQ_CAP - 32);
                     while (need) {
                         const int l = __ffs(need) - 1;
                         need &= need - 1;
-                        const int n_l = __shfl_sync(VQ_FULL_MASK, cnt, l);
+                        const int n_l = __shfl_sync(VQ_FULL_MASK, (int)cnt, l);
                         float thr_l;
                         const int m_l = warp_prune_list(warp_lists + (size_t)l * VQ_CAP, n_l, k, lane, thr_l);
-                        if (lane == l) { cnt = m_l; thr = thr_l; }
+                        // never loosen a primed threshold
+                        if (lane == l) { cnt = (uint32_t)m_l; thr = fmaxf(thr, thr_l); }
                     }
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_field + as * BLOCK_N + cb * 32, v);
+                    tmem_ld32(tcol0 + cb * 32, v);
                     tmem_ld_wait();
-                    if (cb == BLOCK_N / 32 - 1) {
+                    if (cb == EPI_COLS / 32 - 1) {
                         // all of this warp's reads of the accumulator are done: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                        if (lane == 0) {
+                            if (CG == 1) mbar_arrive(&tmem_empty_bar[as]);
+                            else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                        }
                     }
-                    const uint32_t rbase = row0 + cb * 32;
-                    if (cb * 32 + 32 <= n_valid) {
+                    // fast reject: the block's maximum against the threshold (NaN never wins an fmaxf)
+                    float mx = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float s = __uint_as_float(v[j]);
-                            if (s > thr) {
-                                __stcg(my_list + cnt, (unsigned long long)make_key(s, rbase + j));
-                                cnt++;
-                            }
-                        }
-                    } else {
-                        const int lim = n_valid - cb * 32;  // rows past the end of the corpus are TMA zero fill
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float s = __uint_as_float(v[j]);
-                            if (j < lim && s > thr) {
-                                __stcg(my_list + cnt, (unsigned long long)make_key(s, rbase + j));
-                                cnt++;
-                            }
-                        }
+                    for (int j = 2; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    if (__any_sync(VQ_FULL_MASK, mx > thr)) {
+                        const uint32_t rbase = row0 + cb * 32;
+                        // rows past the end of the corpus are TMA zero fill: lim masks them (32 = all valid)
+                        const int lim = min(32, n_valid - cb * 32);
+                        if (lim == 32) push_block<0, 32>(my_list, cnt, v, thr, rbase, 32);
+                        else push_block<0, 32>(my_list, cnt, v, thr, rbase, lim);
                     }
                 }
             }
-            // end of the work item: every list is sorted, cut to k, and its length published
-            __syncwarp();
-            for (int l = 0; l < 32; l++) {
-                const int n_l = __shfl_sync(VQ_FULL_MASK, cnt, l);
-                float thr_l;
-                const int m_l = warp_prune_list(warp_lists + (size_t)l * VQ_CAP, n_l, k, lane, thr_l);
-                if (lane == l) cnt = m_l;
-            }
-            p.counts[(size_t)chunk * p.nq_pad + q] = active ? cnt : 0;
+            // end of the work item: publish the (unsorted) list length; the pass's merge kernel sorts
+            p.counts[list_set * p.nq_pad + q] = active ? (int)cnt : 0;
         }
     }
 
@@ -418,33 +439,33 @@ static int launch_cg(const CUtensorMap& tq, const CUtensorMap& tx, const TcParam
 
 }  // namespace tc
 
-// Plans the (m_tile, chunk) decomposition for nq queries over n_rows corpus rows on n_sms SMs.
+// Plans the (query tile, residue class) decomposition for nq queries over n_rows corpus rows on n_sms SMs.
 void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan) {
     int cg = force_cg;
     if (cg != 1 && cg != 2) cg = (nq > tc::BLOCK_Q) ? 2 : 1;
     const int n_clusters_max = n_sms / cg;
     const int m_tiles = (nq + tc::BLOCK_Q * cg - 1) / (tc::BLOCK_Q * cg);
     const int n_tiles = (int)((n_rows + tc::BLOCK_N - 1) / tc::BLOCK_N);
-    // smallest chunk count whose (m_tile, chunk) items spread evenly over the clusters
+    // smallest number of residue classes G whose m_tiles * G items spread evenly over the clusters;
+    // cost model: the slowest cluster runs rounds * ceil(n_tiles / G) tiles
     int best_c = 1;
     double best_eff = 0.0;
-    const int c_max = n_tiles < 4 * n_clusters_max ? (n_tiles > 0 ? n_tiles : 1) : 4 * n_clusters_max;
+    int c_max = n_tiles < 4 * n_clusters_max ? (n_tiles > 0 ? n_tiles : 1) : 4 * n_clusters_max;
+    if (c_max > 448) c_max = 448;  // 2 list sets per class, the merge kernel takes at most 1023 sets
     for (int c = 1; c <= c_max; c++) {
         const int tpc = (n_tiles + c - 1) / c;
-        const int c_eff = (n_tiles + tpc - 1) / tpc;
-        const long long items = (long long)m_tiles * c_eff;
+        const long long items = (long long)m_tiles * c;
         const long long rounds = (items + n_clusters_max - 1) / n_clusters_max;
-        // cost model: rounds * tiles_per_chunk tile-times for the slowest cluster
         const double eff = (double)m_tiles * n_tiles / ((double)rounds * tpc * n_clusters_max);
         if (eff > best_eff + 0.02) { best_eff = eff; best_c = c; }
         if (best_eff > 0.97) break;
     }
-    const int tpc = n_tiles > 0 ? (n_tiles + best_c - 1) / best_c : 1;
     plan->cg = cg;
     plan->m_tiles = m_tiles;
     plan->n_tiles = n_tiles;
-    plan->tiles_per_chunk = tpc;
-    plan->n_chunks = n_tiles > 0 ? (n_tiles + tpc - 1) / tpc : 1;
+    plan->n_chunks = best_c;
+    plan->tiles_per_chunk = n_tiles > 0 ? (n_tiles + best_c - 1) / best_c : 1;
+    plan->list_sets = best_c * tc::EPI_HALVES;
     plan->nq_pad = m_tiles * tc::BLOCK_Q * cg;
     const long long items = (long long)plan->m_tiles * plan->n_chunks;
     plan->n_clusters = (int)(items < n_clusters_max ? items : n_clusters_max);
@@ -453,11 +474,11 @@ void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan) {
 
 // q16: [nq, ld_q] 16-bit queries (device); x16: [n_rows, ld_x] 16-bit corpus (device)
 int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
-                   const TcPlan& plan, uint64_t* lists, int* counts, cudaStream_t stream) {
+                   const TcPlan& plan, const TcPass& pass, uint64_t* lists, int* counts, cudaStream_t stream) {
     if (k < 1 || k > VQ_KMAX) return -2;
     if (n_rows <= 0 || nq <= 0) return 0;
     CUtensorMap tq, tx;
-    int rc = tc::encode_2d(&tq, q16, dtype, (uint64_t)nq, (uint64_t)d, (uint64_t)ld_q, tc::BLOCK_Q);
+    int rc = tc::encode_2d(&tq, q16, dtype, (uint64_t)plan.nq_pad, (uint64_t)d, (uint64_t)ld_q, tc::BLOCK_Q);  // q16 holds nq_pad rows
     if (rc) return rc;
     rc = tc::encode_2d(&tx, x16, dtype, (uint64_t)n_rows, (uint64_t)d, (uint64_t)ld_x, (uint32_t)(tc::BLOCK_N / plan.cg));
     if (rc) return rc;
@@ -470,7 +491,11 @@ int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long
     p.k = k;
     p.num_kb = (d + tc::BLOCK_K - 1) / tc::BLOCK_K;
     p.m_tiles = plan.m_tiles;
-    p.n_tiles = plan.n_tiles;
+    p.n_tiles = pass.tile_end;
+    p.tile_begin = pass.tile_begin;
+    p.list_set_base = pass.list_set_base;
+    p.init_thr = pass.init_thr;
+    p.init_thr_stride = pass.init_thr_stride;
     p.n_chunks = plan.n_chunks;
     p.tiles_per_chunk = plan.tiles_per_chunk;
     // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format bf16 = 1 / f16 = 0 (bits 7-9, 10-12), both K-major
