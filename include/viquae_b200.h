@@ -97,6 +97,11 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
 int vq_index_search_host(vq_index* idx, const float* q_host, int nq, int l2norm_q, int k, float* out_scores_host,
                          int64_t* out_ids_host);
 
+/* meerqat.ir.search.L2norm (search.py:43-46) / the dtype cast of np.array(queries, dtype=float32)
+ * (search.py:143) as a standalone device operation: src [n, d] -> dst [n, d], optional row-wise
+ * x / ||x||_2 (no epsilon: a zero row becomes NaN like the reference).  Device pointers. */
+int vq_prep_rows(const void* src, int src_dtype, void* dst, int dst_dtype, uint64_t n, int d, int l2norm, void* stream);
+
 /* Cross-GPU k-way merge after the all-gather of per-shard results.  Device pointers:
  * scores float32 / ids int64 [n_lists, nq, k_in] (id < 0 = padding) -> [nq, k_out]. */
 int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out, float* out_scores,

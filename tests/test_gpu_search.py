@@ -1,0 +1,234 @@
+"""Parity of the CUDA path against the oracle — every call goes through the C ABI
+(B200FlatIndex -> libviquae_b200.so).  Integer work (ids, fp32-mode scores) must be bit-exact;
+16-bit modes are compared on the SAME quantised inputs within the tolerance BASELINE.json states:
+scores within 2e-3 relative, top-k overlap >= 99.9 %, id differences only at (near-)ties."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, flat_ip
+
+pytestmark = pytest.mark.gpu
+REL_TOL_16 = 2e-3   # north star: bf16/fp16 scores within 2e-3 relative
+MIN_OVERLAP = 0.999  # north star: top-100 overlap >= 99.9 %
+
+
+def make(N, nq, d, dtype, seed=1, dist="normal"):
+    rng = np.random.default_rng(seed)
+    if dist == "dpr":  # DPR-like: common offset, scores cluster near 71 +- 2
+        m = rng.standard_normal(d).astype(np.float32) * (8.0 / np.sqrt(d))
+        X = m + 0.35 * rng.standard_normal((N, d), dtype=np.float32)
+        Q = m * 8.9 + 0.35 * rng.standard_normal((nq, d), dtype=np.float32)
+    else:
+        X = rng.standard_normal((N, d), dtype=np.float32)
+        Q = rng.standard_normal((nq, d), dtype=np.float32)
+    if dtype == "bf16":
+        X, Q = flat_ip.bf16_round(X), flat_ip.bf16_round(Q)
+    elif dtype == "f16":
+        X, Q = flat_ip.fp16_round(X), flat_ip.fp16_round(Q)
+    return X, Q
+
+
+def engine(X, dtype, variant=None, **kw):
+    from viquae_b200.index import B200FlatIndex
+    idx = B200FlatIndex(d=X.shape[1], dtype=dtype, device=0, variant=variant, **kw)
+    idx.add(X)
+    return idx
+
+
+def check16(idx, X, Q, k):
+    res = idx.search_batch(Q, k)
+    D, I = np.asarray(res.total_scores), np.asarray(res.total_indices)
+    Dr, Ir = flat_ip.flat_ip_search(Q, X, k)
+    cmp = flat_ip.compare_results(Dr, Ir, D, I, rel_tol=REL_TOL_16)
+    assert cmp["real_mismatches"] == 0 and cmp["overlap"] >= MIN_OVERLAP and cmp["max_rel_err"] <= REL_TOL_16, cmp
+    assert np.all(np.diff(D, axis=1) <= 0), "scores must be descending"
+    assert D.dtype == np.float32 and I.dtype.kind == "i"
+    return D, I
+
+
+@pytest.mark.parametrize("N,nq,d,k", [(5000, 70, 768, 100), (3001, 130, 100, 10), (20000, 3, 512, 128), (257, 1, 8, 5)])
+def test_fp32_mode_is_bit_exact(N, nq, d, k):
+    X, Q = make(N, nq, d, "f32")
+    idx = engine(X, "f32")
+    res = idx.search_batch(Q, k)
+    Dr, Ir = c_oracle.flat_ip(Q, X, k)
+    assert np.array_equal(np.asarray(res.total_indices), Ir)
+    assert np.array_equal(np.asarray(res.total_scores).view(np.uint32), Dr.view(np.uint32)), "fixed reduction order: scores bit-exact"
+
+
+@pytest.mark.parametrize("variant,N,nq,d,k,dtype", [
+    ("tc_cg1", 5000, 70, 768, 100, "bf16"),
+    ("tc_cg1", 70001, 100, 768, 100, "bf16"),
+    ("tc_cg2", 5000, 300, 768, 100, "bf16"),
+    ("tc_cg2", 70000, 1250, 768, 100, "bf16"),       # validation-size batch (BASELINE configs[0] queries)
+    ("tc_cg2", 300000, 300, 768, 100, "bf16"),       # multi-pass threshold priming
+    ("tc_cg1", 300100, 100, 512, 10, "f16"),         # CLIP/ArcFace dimension, fp16
+    ("tc_cg2", 600000, 130, 64, 128, "bf16"),        # k at the supported maximum
+    ("tc_cg1", 9000, 33, 104, 7, "bf16"),            # d not a multiple of 64 (row stride padded to 8)
+    ("stream", 20000, 1, 768, 100, "bf16"),
+    ("stream", 20000, 20, 768, 100, "bf16"),
+    ("stream", 5000, 32, 512, 10, "f16"),
+    (None, 40000, 256, 768, 100, "bf16"),            # the reference's call granularity: 256 queries per call
+])
+def test_16bit_modes_match_oracle_on_same_quantised_inputs(variant, N, nq, d, k, dtype):
+    X, Q = make(N, nq, d, dtype)
+    check16(engine(X, dtype, variant), X, Q, k)
+
+
+def test_dpr_like_scores_and_l2norm_factory():
+    X, Q = make(30000, 64, 768, "bf16", dist="dpr")
+    check16(engine(X, "bf16"), X, Q, 100)
+    # "L2norm,Flat": rows normalised on ingest, queries on search (cosine); compare in fp32 mode against the oracle
+    X, Q = make(4000, 40, 512, "f32", seed=3)
+    idx = engine(X, "f32", string_factory="L2norm,Flat")
+    res = idx.search_batch(Q, 20)
+    Dr, Ir = flat_ip.flat_ip_search(flat_ip.l2norm(Q), flat_ip.l2norm(X), 20)
+    cmp = flat_ip.compare_results(Dr, Ir, res.total_scores, res.total_indices, rel_tol=1e-5, abs_tol=1e-6)
+    assert cmp["real_mismatches"] == 0 and cmp["max_rel_err"] < 1e-4 and np.abs(np.asarray(res.total_scores)).max() <= 1.0001, cmp
+
+
+def test_edge_cases():
+    from viquae_b200.index import B200FlatIndex
+    X, Q = make(50, 4, 64, "bf16")
+    idx = engine(X, "bf16")
+    res = idx.search_batch(Q, 100)          # N < k: padded with (-FLT_MAX, -1)
+    I, D = np.asarray(res.total_indices), np.asarray(res.total_scores)
+    assert (I[:, 50:] == -1).all() and (D[:, 50:] == np.finfo(np.float32).min).all() and (I[:, :50] >= 0).all()
+    Dr, Ir = flat_ip.flat_ip_search(Q, X, 100)
+    assert flat_ip.compare_results(Dr, Ir, D, I, rel_tol=REL_TOL_16)["real_mismatches"] == 0
+    assert idx.search_batch(np.zeros((0, 64), np.float32), 5).total_scores.shape == (0, 5)   # empty batch
+    with pytest.raises(ValueError):
+        idx.search_batch(np.zeros(64, np.float32), 5)                                        # datasets/search.py:380-381
+    with pytest.raises(ValueError):
+        idx.search_batch(np.zeros((2, 63), np.float32), 5)
+    from viquae_b200._lib import EngineError
+    with pytest.raises(EngineError):
+        idx.search_batch(Q, 129)                                                             # k > 128: refused, not approximated
+    one = idx.search(Q[0], 7)                                                                 # FaissIndex.search: one vector
+    assert len(one.scores) == 7 and np.array_equal(np.asarray(one.indices), I[0, :7])
+    empty = B200FlatIndex(d=64, dtype="bf16")
+    r = empty.search_batch(Q, 3)
+    assert (np.asarray(r.total_indices) == -1).all()
+    # exact ties: duplicated rows -> lower id first, on every kernel family
+    Xd = np.repeat(X[:10], 3, axis=0)
+    for dtype, variant in (("bf16", "tc_cg1"), ("bf16", "stream"), ("f32", None)):
+        r = engine(Xd, dtype, variant).search_batch(Q, 30)
+        ids = np.asarray(r.total_indices)
+        s = np.asarray(r.total_scores)
+        for row_s, row_i in zip(s, ids):
+            for a in range(0, 30, 3):
+                assert row_s[a] == row_s[a + 1] == row_s[a + 2] and row_i[a] < row_i[a + 1] < row_i[a + 2]
+    # NaN rows are never selected (FAISS: a candidate enters only if strictly greater)
+    Xn = X.copy(); Xn[7] = np.nan
+    r = engine(Xn, "f32").search_batch(Q, 50)
+    assert 7 not in np.asarray(r.total_indices) and (np.asarray(r.total_indices)[:, 49] == -1).all()
+
+
+def test_incremental_add_growth_save_load(tmp_path):
+    X, Q = make(7000, 16, 96, "bf16")
+    from viquae_b200.index import B200FlatIndex
+    idx = B200FlatIndex(d=96, dtype="bf16")
+    for a in range(0, 7000, 1000):          # the reference adds 1000-row batches (datasets/search.py:311-313)
+        idx.add(X[a:a + 1000])
+    assert len(idx) == 7000
+    D, I = check16(idx, X, Q, 10)
+    idx.add(torch.from_numpy(X[:100]).cuda().to(torch.bfloat16))   # device-resident ingest
+    assert len(idx) == 7100
+    idx.save(tmp_path / "kb.index")
+    idx2 = B200FlatIndex.load(tmp_path / "kb.index")
+    r1, r2 = idx.search_batch(Q, 10), idx2.search_batch(Q, 10)
+    assert np.array_equal(r1.total_indices, r2.total_indices) and np.array_equal(r1.total_scores, r2.total_scores)
+    assert np.array_equal(idx.reconstruct_n(5, 3), X[5:8])
+
+
+def test_device_resident_search_and_cross_shard_merge():
+    from viquae_b200.index import B200FlatIndex, merge_topk
+    X, Q = make(9000, 40, 128, "bf16")
+    full = engine(X, "bf16")
+    s_full, i_full = full.search_tensors(torch.from_numpy(Q).cuda(), 50)
+    parts = []
+    for a, b in ((0, 3000), (3000, 6500), (6500, 9000)):
+        sh = B200FlatIndex(d=128, dtype="bf16", id_offset=a)
+        sh.add(X[a:b])
+        parts.append(sh.search_tensors(torch.from_numpy(Q).cuda().to(torch.bfloat16), 50))
+    s_m, i_m = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    cmp = flat_ip.compare_results(s_full.cpu().numpy(), i_full.cpu().numpy(), s_m.cpu().numpy(), i_m.cpu().numpy(), rel_tol=1e-5)
+    assert cmp["real_mismatches"] == 0 and cmp["overlap"] == 1.0, cmp
+    Dm, Im = flat_ip.merge_topk([p[0].cpu().numpy() for p in parts], [p[1].cpu().numpy() for p in parts], 50)
+    assert np.array_equal(Im, i_m.cpu().numpy()) and np.array_equal(Dm, s_m.cpu().numpy())
+
+
+def test_reference_golden_through_knowledgebase_and_searcher(golden_dir, tmp_path):
+    """The toy KB of tests/golden (outputs of the reference's own KnowledgeBase/Searcher) through OUR
+    KnowledgeBase/Searcher with kind=B200, fp32 storage: same ids, same str doc ids, same runs."""
+    from viquae_b200.search import KnowledgeBase, Searcher
+    g = np.load(os.path.join(golden_dir, "search_golden.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "search_golden.json")))
+    k = meta["k"]
+    kb_data = {"text_emb": g["txt"], "image_emb": g["img"]}
+    map_path = tmp_path / "a2p.json"
+    json.dump(meta["mapping"], open(map_path, "wt"))
+    qrels_path = tmp_path / "qrels.json"
+    json.dump({}, open(qrels_path, "wt"))
+    index_kwargs = {"dpr": {"column": "text_emb", "kind": "B200", "key": "q_text", "string_factory": "Flat", "metric_type": 0, "dtype": "f32"},
+                    "clip": {"column": "image_emb", "kind": "B200", "key": "q_image", "string_factory": "L2norm,Flat", "metric_type": 0, "dtype": "f32"}}
+
+    class DictDS(dict):
+        def __len__(self):
+            return len(next(iter(self.values())))
+    kb = KnowledgeBase(dataset=DictDS(kb_data), index_mapping_path=str(map_path), index_kwargs=index_kwargs)
+    assert {n: ix.do_L2norm for n, ix in kb.indexes.items()} == meta["do_L2norm"]
+    s1, i1 = kb.search_batch("dpr", g["q_txt"], k=k)
+    assert np.array_equal(np.asarray(i1), g["dpr_ids"]) and np.allclose(s1, g["dpr_scores"], rtol=1e-5)
+    s2, i2 = kb.search_batch("clip", g["q_img"], k=k)
+    assert np.array_equal(np.asarray(i2), g["clip_ids"]) and np.allclose(s2, g["clip_scores"], rtol=1e-4, atol=1e-6)
+    q_img_list = [None if m else g["q_img"][j].tolist() for j, m in enumerate(g["none_mask"])]
+    s3, i3 = kb.search_batch_if_not_None("clip", q_img_list, k=k)
+    assert [len(x) for x in i3] == meta["if_not_none_lengths"]
+    searcher = Searcher.__new__(Searcher)
+    searcher.k, searcher.kbs, searcher.runs = k, {"kb": kb}, {"dpr": {}, "clip": {}}
+    searcher.qrels, searcher.qnonrels, searcher.reference_kb, searcher.find_relevant = {}, {}, None, None
+    nq = len(g["q_txt"])
+    searcher({"id": [f"q{j}" for j in range(nq)], "q_text": g["q_txt"].tolist(), "q_image": q_img_list})
+    for name in ("dpr", "clip"):
+        for q, ref in meta["runs"][name].items():
+            mine = searcher.runs[name][q]
+            assert list(mine) == list(ref), (name, q)
+            assert np.allclose([float(v) for v in mine.values()], list(ref.values()), rtol=1e-4, atol=1e-6)
+
+
+def test_large_corpus_properties():
+    """Size-independent properties at a size the oracle cannot check in seconds: 2M x 768 bf16 generated on the
+    device.  (i) returned scores equal recomputed dot products of the returned rows, (ii) descending order,
+    (iii) sharding invariance: top-k of the whole == merge of the top-k of two halves, (iv) determinism."""
+    from viquae_b200.index import B200FlatIndex, merge_topk
+    N, d, nq, k = 2_000_000, 768, 1250, 100
+    g = torch.Generator(device="cuda"); g.manual_seed(123)
+    X = torch.randn((N, d), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16)
+    Q = torch.randn((nq, d), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16)
+    idx = B200FlatIndex(d=d, dtype="bf16", capacity=N); idx.add(X)
+    s, i = idx.search_tensors(Q, k)
+    assert (i >= 0).all() and (i < N).all() and (s[:, 1:] <= s[:, :-1]).all()
+    rows = X[i.reshape(-1)].float().reshape(nq, k, d)
+    recomputed = torch.einsum("qkd,qd->qk", rows, Q.float())
+    assert torch.allclose(recomputed, s, rtol=REL_TOL_16, atol=1e-3)
+    # a random sample of rows never beats the k-th returned score
+    sample = torch.randint(0, N, (4096,), device="cuda")
+    assert ((Q.float() @ X[sample].float().T).max(dim=1).values <= s[:, 0] + 1e-3).all()
+    s2, i2 = idx.search_tensors(Q, k)
+    assert torch.equal(i, i2) and torch.equal(s, s2)
+    halves = []
+    for a, b in ((0, N // 2), (N // 2, N)):
+        sh = B200FlatIndex(d=d, dtype="bf16", capacity=b - a, id_offset=a); sh.add(X[a:b])
+        halves.append(sh.search_tensors(Q, k)); sh.close()
+    s_m, i_m = merge_topk(torch.stack([h[0] for h in halves]), torch.stack([h[1] for h in halves]))
+    cmp = flat_ip.compare_results(s.cpu().numpy(), i.cpu().numpy(), s_m.cpu().numpy(), i_m.cpu().numpy(), rel_tol=1e-4)
+    assert cmp["real_mismatches"] == 0 and cmp["overlap"] >= 0.9999, cmp
+    # small batch over the same corpus agrees with the large batch (different kernel variant / pass schedule)
+    s3, i3 = idx.search_tensors(Q[:5], k)
+    cmp = flat_ip.compare_results(s[:5].cpu().numpy(), i[:5].cpu().numpy(), s3.cpu().numpy(), i3.cpu().numpy(), rel_tol=1e-4)
+    assert cmp["real_mismatches"] == 0, cmp

@@ -1,0 +1,135 @@
+"""Host-side logic that needs no GPU: config parsing, sharding arithmetic, run containers, dense
+conversion, metrics, and the experiment configs of the reference (when its checkout is present)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from viquae_b200 import fuse, runs, search, sharded
+from viquae_b200.index import parse_string_factory
+
+
+def test_string_factory_semantics():
+    assert parse_string_factory("Flat", 0) is False
+    assert parse_string_factory("L2norm,Flat", 0) is True
+    assert parse_string_factory("L2norm, Flat", None) is True
+    assert parse_string_factory(None, 0) is False
+    with pytest.raises(ValueError, match="L2"):
+        parse_string_factory(None, None)  # datasets would silently build an L2 index
+    with pytest.raises(ValueError):
+        parse_string_factory("Flat", 1)
+    with pytest.raises(ValueError):
+        parse_string_factory("IVF4096,Flat", 0)
+
+
+def test_index_kind_lookup_by_name():
+    assert search.IndexKind["B200"] is search.IndexKind.B200
+    assert [k.name for k in search.IndexKind][:3] == ["FAISS", "ES", "PYSERINI"]
+    kb = search.KnowledgeBase(load_dataset=False)
+    kb.add_or_load_index(column=None, index_name="dpr", kind="B200", key="q_text", string_factory="L2norm,Flat")
+    assert kb.indexes["dpr"].do_L2norm is True and kb.indexes["dpr"].key == "q_text"
+    with pytest.raises(NotImplementedError):
+        kb.add_or_load_index(column=None, index_name="bm25", kind="ES", key="input")
+    with pytest.raises(KeyError):
+        search.IndexKind["ANNOY"]
+    with pytest.warns(UserWarning):  # legacy dialect keys are tolerated
+        kb.add_or_load_index(column=None, index_name="old", key="q", string_factory="Flat", es=False, kind_str="TEXT", normalization={"mean": 1})
+    with pytest.raises(TypeError):
+        kb.add_or_load_index(column=None, index_name="bad", key="q", string_factory="Flat", nprobe=3)
+
+
+def test_shard_ranges_cover_and_balance():
+    for n, w in ((12_000_000, 8), (10, 3), (7, 8), (0, 2)):
+        r = [sharded.shard_range(n, i, w) for i in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_run_orders_descending_and_roundtrips(tmp_path):
+    r = runs.Run({"q": {"a": 0.1, "b": 0.9, "c": 0.5}}, name="x")
+    assert list(r.run["q"]) == ["b", "c", "a"]
+    r.save(tmp_path / "r.json")
+    assert runs.Run.from_file(tmp_path / "r.json").run == r.run
+
+
+def test_metrics():
+    q = runs.Qrels({"q1": {"a": 1}, "q2": {"z": 1}})
+    r = runs.Run({"q1": {"b": 3.0, "a": 2.0}, "q2": {"x": 1.0}})
+    m = runs.evaluate(q, r, ["mrr@100", "precision@1", "hit_rate@20"])
+    assert m == {"mrr@100": 0.25, "precision@1": 0.0, "hit_rate@20": 0.5}
+
+
+def test_weight_grid_sizes():
+    assert [len(list(fuse.weight_grid(n))) for n in (2, 3, 4)] == [11, 66, 286]
+    assert all(abs(sum(w) - 1) < 1e-9 for w in fuse.weight_grid(3))
+
+
+def test_dense_runs_roundtrip():
+    a = {"q1": {"10": 2.0, "7": 1.0}, "q2": {}}
+    b = {"q1": {"7": 5.0}, "q3": {"1": 0.5}}
+    d = fuse.DenseRuns([a, b])
+    assert d.q_ids == ["q1", "q2", "q3"] and d.scores.shape == (2, 3, 2)
+    assert d.ids[0, 0].tolist() == [10, 7] and d.ids[0, 1].tolist() == [-1, -1] and d.ids[1, 2].tolist() == [1, -1]
+    assert d.decode(7) == "7"
+    d2 = fuse.DenseRuns([{"q": {"doc_a": 1.0, "doc_b": 2.0}}])
+    assert d2.decode(int(d2.ids[0, 0, 0])) == "doc_a"
+
+
+def test_searcher_postprocessing_matches_reference_golden(golden_dir):
+    """Searcher._record vs the runs the reference's own Searcher.__call__ produced (search.py:413-440)."""
+    g = np.load(os.path.join(golden_dir, "search_golden.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "search_golden.json")))
+
+    class KB:
+        index_mapping = {int(k): v for k, v in meta["mapping"].items()}
+        many2one = None
+    s = search.Searcher.__new__(search.Searcher)
+    s.k = meta["k"]
+    for q in range(g["dpr_ids"].shape[0]):
+        run_q = {}
+        s._record(KB, run_q, g["dpr_scores"][q], g["dpr_ids"][q])
+        ref = meta["runs"]["dpr"][f"q{q}"]
+        assert list(run_q) == list(ref)
+        assert np.allclose([float(v) for v in run_q.values()], list(ref.values()), rtol=1e-6)
+    KB.many2one = "max"
+    KB.index_mapping = {0: [5], 1: [5], 2: [6]}
+    run_q = {}
+    s._record(KB, run_q, [3.0, 2.0, 1.0], [1, 0, 2])
+    assert run_q == {"5": 3.0, "6": 1.0}
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_reference_experiment_configs_parse():
+    """Every dense index entry of the shipped IR configs is accepted (legacy keys tolerated), SURVEY §4."""
+    paths = glob.glob(os.path.join(REFERENCE, "experiments", "ir", "**", "*.json"), recursive=True)
+    n_dense = 0
+    for path in paths:
+        try:
+            cfg = json.load(open(path))
+        except Exception:
+            continue
+        if not isinstance(cfg, dict) or "kb_kwargs" not in cfg:
+            continue
+        for kb_path, kb_kwarg in cfg["kb_kwargs"].items():
+            for name, ik in kb_kwarg.get("index_kwargs", {}).items():
+                ik = dict(ik)
+                if ik.get("es") or ik.get("kind") in ("ES", "PYSERINI"):
+                    continue
+                ik.pop("column", None)
+                kb = search.KnowledgeBase(load_dataset=False)
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    if ik.get("string_factory") is None and ik.get("metric_type") is None:
+                        ik["metric_type"] = 0
+                    kb.add_or_load_index(column=None, index_name=name, **ik)
+                assert name in kb.indexes
+                n_dense += 1
+    assert n_dense >= 5

@@ -1,0 +1,118 @@
+"""The oracle against the golden fixtures produced by the reference's own Python layer, against
+itself (numpy vs C restatement) and on the edge cases FAISS IndexFlatIP defines."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, flat_ip, fuse_oracle
+
+
+def test_search_golden_matches_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "search_golden.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "search_golden.json")))
+    k = meta["k"]
+    D, I = flat_ip.flat_ip_search(g["q_txt"], g["txt"], k)
+    assert np.array_equal(I, g["dpr_ids"]) and np.allclose(D, g["dpr_scores"], rtol=1e-6)
+    # "L2norm,Flat": corpus normalised on add, queries normalised by KnowledgeBase.search_batch and again by FAISS
+    D2, I2 = flat_ip.flat_ip_search(flat_ip.l2norm(g["q_img"]), flat_ip.l2norm(g["img"]), k, l2norm_queries=True)
+    assert np.array_equal(I2, g["clip_ids"]) and np.allclose(D2, g["clip_scores"], rtol=1e-5, atol=1e-6)
+    assert meta["do_L2norm"] == {"dpr": False, "clip": True}
+    assert np.all(np.diff(g["dpr_scores"], axis=1) <= 0), "reference returns descending scores"
+    assert g["dpr_ids"].dtype == np.int64 and g["dpr_scores"].dtype == np.float32
+
+
+def test_c_oracle_equals_numpy_oracle():
+    rng = np.random.default_rng(3)
+    Q = rng.standard_normal((9, 48), dtype=np.float32)
+    X = rng.standard_normal((3000, 48), dtype=np.float32)
+    D, I = flat_ip.flat_ip_search(Q, X, 17)
+    Dc, Ic = c_oracle.flat_ip(Q, X, 17)
+    assert np.array_equal(I, Ic)
+    assert np.allclose(D, Dc, rtol=1e-5, atol=1e-6)  # BLAS vs fixed-order fmaf: summation order only
+    Df, If = flat_ip.flat_ip_search_fast(Q, X, 17)
+    assert np.array_equal(I, If)
+
+
+def test_c_oracle_is_fixed_order_fma():
+    rng = np.random.default_rng(4)
+    q = rng.standard_normal(37).astype(np.float32)
+    x = rng.standard_normal((5, 37)).astype(np.float32)
+    D, I = c_oracle.flat_ip(q[None], x, 5)
+    for score, row in zip(D[0], I[0]):
+        acc = 0.0  # float64 emulation of fmaf: exact product, one rounding per step
+        for j in range(37):
+            acc = float(np.float32(np.float64(q[j]) * np.float64(x[row, j]) + np.float64(np.float32(acc))))
+        assert np.float32(acc) == score
+
+
+def test_padding_ties_and_unselectable_values():
+    X = np.array([[1, 0], [1, 0], [0, 1], [np.nan, 0], [-np.inf, 0]], dtype=np.float32)
+    Q = np.array([[1, 0]], dtype=np.float32)
+    for D, I in (flat_ip.flat_ip_search(Q, X, 6), c_oracle.flat_ip(Q, X, 6)):
+        assert I[0].tolist()[:3] == [0, 1, 2], "ties: lower id first"
+        assert I[0].tolist()[3:] == [-1, -1, -1], "NaN / -inf are never selected; padding id is -1"
+        assert np.all(D[0][3:] == np.finfo(np.float32).min)
+    D, I = flat_ip.flat_ip_search(np.zeros((0, 2), np.float32), X, 3)
+    assert D.shape == (0, 3)
+    with pytest.raises(ValueError):
+        flat_ip.flat_ip_search(np.zeros(2, np.float32), X, 3)  # datasets/search.py:380-381
+
+
+def test_l2norm_zero_row_is_nan_like_reference():
+    out = flat_ip.l2norm(np.array([[3, 4], [0, 0]], np.float32))
+    assert np.allclose(out[0], [0.6, 0.8]) and np.isnan(out[1]).all()
+    assert np.allclose(c_oracle.l2norm(np.array([[3, 4]], np.float32)), [[0.6, 0.8]])
+
+
+def test_bf16_rounding_matches_torch():
+    import torch
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 100
+    assert np.array_equal(flat_ip.bf16_round(x), torch.from_numpy(x).to(torch.bfloat16).float().numpy())
+    bits = c_oracle.to_bf16_bits(x)
+    assert np.array_equal(bits, torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))
+
+
+def test_merge_topk_is_topk_of_union():
+    rng = np.random.default_rng(5)
+    Q = rng.standard_normal((6, 16), dtype=np.float32)
+    X = rng.standard_normal((900, 16), dtype=np.float32)
+    D, I = flat_ip.flat_ip_search(Q, X, 20)
+    parts = [flat_ip.flat_ip_search(Q, X[a:b], 20, id_offset=a) for a, b in ((0, 300), (300, 650), (650, 900))]
+    Dm, Im = flat_ip.merge_topk([p[0] for p in parts], [p[1] for p in parts], 20)
+    assert np.array_equal(I, Im) and np.array_equal(D, Dm)
+
+
+# ---------------------------------------------------------------- fusion
+def test_fusion_golden_default_minimum(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "fusion_golden.json")))
+    mine = fuse_oracle.default_minimum(g["runs"])
+    assert mine == g["after_defmin"], "restated default_minimum differs from the reference's output"
+    assert all(len(r) == 0 for r in (mine[2][q] for q in ("q0", "q3")))  # runs without results stay empty
+
+
+def test_fusion_golden_gzmuv(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "fusion_golden.json")))
+    for src, key in ((g["after_defmin"], "gzmuv_after_defmin"), (g["runs"], "gzmuv_raw")):
+        for run, ref in zip(src, g[key]):
+            mine = fuse_oracle.gzmuv_norm(run)
+            assert mine.keys() == ref.keys()
+            for q in ref:
+                assert mine[q].keys() == ref[q].keys()
+                for d in ref[q]:
+                    assert abs(mine[q][d] - ref[q][d]) <= 1e-12 * max(1.0, abs(ref[q][d]))
+
+
+def test_survey_known_answer_gzmuv():
+    out = fuse_oracle.gzmuv_norm({"q1": {"a": 3.0, "b": 1.0}, "q2": {"c": 5.0}})
+    assert abs(out["q1"]["a"]) < 1e-12 and abs(out["q1"]["b"] + 1.224744871) < 1e-8 and abs(out["q2"]["c"] - 1.224744871) < 1e-8
+
+
+def test_wsum_union_and_order():
+    a = {"q": {"1": 1.0, "2": 0.5}}
+    b = {"q": {"2": 1.0, "3": 0.25}}
+    fused = fuse_oracle.wsum([a, b], [0.5, 0.5])
+    assert list(fused["q"].items()) == [("2", 0.75), ("1", 0.5), ("3", 0.125)]
+    z = fuse_oracle.zmuv_norm({"q": {"1": 2.0}})
+    assert z["q"]["1"] == 0.0  # single result: std 0 -> denominator 1e-9

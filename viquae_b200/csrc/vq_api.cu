@@ -447,6 +447,14 @@ int vq_index_search_host(vq_index* idx, const float* q_host, int nq, int l2norm_
     return VQ_OK;
 }
 
+int vq_prep_rows(const void* src, int src_dtype, void* dst, int dst_dtype, uint64_t n, int d, int l2norm, void* stream) {
+    if ((!src || !dst) && n) return fail(VQ_ERR_INVALID, "vq_prep_rows: null pointer");
+    if (!dtype_ok(src_dtype) || !dtype_ok(dst_dtype) || d <= 0) return fail(VQ_ERR_INVALID, "vq_prep_rows: bad arguments");
+    int rc = vq::prep_rows_launch(src, src_dtype, d, dst, dst_dtype, d, (long long)n, d, l2norm, (cudaStream_t)stream);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_prep_rows: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
 int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out, float* out_scores,
                   int64_t* out_ids, void* stream) {
     if (!scores || !ids || !out_scores || !out_ids || n_lists < 1 || nq < 0) return fail(VQ_ERR_INVALID, "vq_merge_topk: bad arguments");

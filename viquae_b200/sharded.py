@@ -57,8 +57,12 @@ class ShardedFlatIndex:
         s_all = torch.empty((self.world_size, nq, k), dtype=s_loc.dtype, device=s_loc.device)
         i_all = torch.empty((self.world_size, nq, k), dtype=i_loc.dtype, device=i_loc.device)
         # two small all-gathers (scores f32, ids i64): nq*k*12 B per rank, latency-bound on NVSwitch
-        self.dist.all_gather_into_tensor(s_all, s_loc.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(i_all, i_loc.contiguous(), group=self.group)
+        if self.dist.get_backend(self.group) == "nccl":
+            self.dist.all_gather_into_tensor(s_all, s_loc.contiguous(), group=self.group)
+            self.dist.all_gather_into_tensor(i_all, i_loc.contiguous(), group=self.group)
+        else:  # gloo (CPU tests): same exchange through the list form
+            self.dist.all_gather(list(s_all.unbind(0)), s_loc.contiguous(), group=self.group)
+            self.dist.all_gather(list(i_all.unbind(0)), i_loc.contiguous(), group=self.group)
         return self._merge(s_all, i_all, k)
 
     def search_batch(self, queries, k: int = 100):
