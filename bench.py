@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--variant", default=None, choices=[None, "auto", "tc_cg1", "tc_cg2", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-rows", type=int, default=600_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="corpus rows of the CPU sample (default: 1.5M inline, 3M for --impl reference)")
     return ap.parse_args()
 
 
@@ -144,7 +144,7 @@ def run_reference(args):
     if rank != 0:
         return
     device = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
-    times, scale, cores, sample_rows = cpu_port_sample(args, device, args.cpu_sample_rows, repeats=max(1, args.steps),
+    times, scale, cores, sample_rows = cpu_port_sample(args, device, args.cpu_sample_rows or 3_000_000, repeats=max(1, args.steps),
                                                        warmup=max(0, min(args.warmup, 1)))
     step_s = sum(times) / len(times) * scale
     value = args.nq / step_s
@@ -294,7 +294,18 @@ def run_ours(args):
             roof = {"bound": "hbm", "achieved": bytes_ / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["peak_source"] = f"{peaks_src} (MEASURED_PEAKS.json burst figure: kernel timed alone)" if peaks_src == "measured" else "fallback (B200_PROFILING.md)"
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch(es), from the committed
+        # `ncu --set full` capture of this same workload (profiles/traffic.json); null for other workloads
         roof["traffic"] = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tr = json.load(f)
+            key = f"nq{args.nq}_rows{args.rows}_d{args.dim}_{args.dtype}_gpus{world}"
+            if key in tr:
+                roof["traffic"] = tr[key]["dram_bytes_per_launch"]
+                roof["traffic_source"] = tr[key]["source"]
+        except Exception:
+            pass
         roof["kernel"] = {"f32": "f32_topk_kernel"}.get(args.dtype, "stream_topk_kernel" if (args.variant == "stream" or (args.variant in (None, "auto") and args.nq <= 32)) else "tc_topk_kernel")
         roof["kernel_ms"] = kern_ms
         roof["kernel_launches_timed"] = nl.value
@@ -312,7 +323,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                times, scale, cores, sample_rows = cpu_port_sample(args, device, args.cpu_sample_rows, repeats=1, warmup=0)
+                times, scale, cores, sample_rows = cpu_port_sample(args, device, args.cpu_sample_rows or 1_500_000, repeats=1, warmup=0)
                 step_s = times[0] * scale
                 line["cpu_baseline"] = {
                     "value": args.nq / step_s, "unit": "queries/s", "cores": cores, "kind": "port",
