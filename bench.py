@@ -286,7 +286,11 @@ def run_ours(args):
         flops = 2.0 * args.nq * local_rows * args.dim
         bytes_ = local_rows * args.dim * (4 if args.dtype == "f32" else 2) + args.nq * args.dim * 2 + args.nq * k * 12
         ridge_tensor = args.nq > 211 and args.dtype != "f32"
-        if ridge_tensor:
+        if args.dtype == "f32":
+            # exact mode is SIMT FFMA-bound: 148 SMs x 128 FMA/clk x 2 flop at the max SM clock (no measured peak for it)
+            peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+            roof = {"bound": "fp32-ffma", "achieved": flops / (kern_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s"}
+        elif ridge_tensor:
             peak = float(peaks.get("bf16_tflops", 1590.0))
             roof = {"bound": "tensor", "achieved": flops / (kern_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s"}
         else:

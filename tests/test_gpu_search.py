@@ -232,3 +232,46 @@ def test_large_corpus_properties():
     s3, i3 = idx.search_tensors(Q[:5], k)
     cmp = flat_ip.compare_results(s[:5].cpu().numpy(), i[:5].cpu().numpy(), s3.cpu().numpy(), i3.cpu().numpy(), rel_tol=1e-4)
     assert cmp["real_mismatches"] == 0, cmp
+
+
+def test_hf_dataset_dispatch_and_dataset_search_with_fusion(tmp_path):
+    """HF datasets integration: the engine registered in Dataset._indexes serves Dataset.search_batch
+    (datasets/search.py:713-733), and dataset_search() maps a query dataset, writes the runs and fuses them."""
+    datasets = pytest.importorskip("datasets")
+    from viquae_b200.search import KnowledgeBase, dataset_search
+    rng = np.random.default_rng(9)
+    n, d1, d2, nq, k = 3000, 64, 32, 40, 20
+    txt = rng.standard_normal((n, d1)).astype(np.float32)
+    img = rng.standard_normal((n, d2)).astype(np.float32)
+    kb_ds = datasets.Dataset.from_dict({"text_emb": txt.tolist(), "image_emb": img.tolist()})
+    kb_path = tmp_path / "kb"
+    kb_ds.save_to_disk(str(kb_path))
+    kb = KnowledgeBase(str(kb_path), index_kwargs={"dpr": {"column": "text_emb", "kind": "B200", "key": "q_text", "string_factory": "Flat",
+                                                            "metric_type": 0, "dtype": "f32"}})
+    q = rng.standard_normal((nq, d1)).astype(np.float32)
+    res = kb.dataset.search_batch("dpr", q, k)              # HF entry point -> B200FlatIndex.search_batch
+    Dr, Ir = c_oracle.flat_ip(q, txt, k)
+    assert np.array_equal(np.asarray(res.total_indices), Ir)
+    # full pipeline: two indexes, qrels from the oracle's top-1 of the text index, fusion applied with fixed weights
+    qi = rng.standard_normal((nq, d2)).astype(np.float32)
+    queries = datasets.Dataset.from_dict({"id": [f"q{j}" for j in range(nq)], "q_text": q.tolist(), "q_image": qi.tolist(),
+                                          "output": [{"original_answer": "", "answer": []}] * nq})
+    qrels = {f"q{j}": {str(int(Ir[j, 0])): 1} for j in range(nq)}
+    json.dump(qrels, open(tmp_path / "qrels.json", "wt"))
+    out = tmp_path / "metrics"
+    searcher = dataset_search(
+        queries, k=k, metric_save_path=out, map_kwargs={"batch_size": 16},
+        kb_kwargs={str(kb_path): {"index_kwargs": {
+            "dpr": {"column": "text_emb", "kind": "B200", "key": "q_text", "string_factory": "Flat", "metric_type": 0, "dtype": "f32"},
+            "clip": {"column": "image_emb", "key": "q_image", "string_factory": "L2norm,Flat", "metric_type": 0}}}},
+        qrels=str(tmp_path / "qrels.json"),
+        fusion_kwargs={"subcommand": "test", "subcommand_kwargs": {"best_params": {"weights": [0.8, 0.2]}}, "norm": "zmuv", "defmin": True})
+    assert (out / "dpr.json").exists() and (out / "clip.json").exists() and (out / "test_run.json").exists() and (out / "metrics.json").exists()
+    metrics = json.load(open(out / "metrics.json"))
+    assert metrics["dpr"]["mrr@100"] == 1.0 and metrics["dpr"]["precision@1"] == 1.0
+    fused = json.load(open(out / "test_run.json"))
+    from oracle import fuse_oracle
+    ref = fuse_oracle.fuse([searcher.runs["dpr"].run, searcher.runs["clip"].run], [0.8, 0.2], norm="zmuv", defmin=True)
+    for qid in ("q0", "q7", "q39"):
+        assert set(fused[qid]) == set(ref[qid])
+        assert np.allclose([fused[qid][d_] for d_ in ref[qid]], list(ref[qid].values()), rtol=1e-9, atol=1e-9)
