@@ -12,49 +12,87 @@
 namespace vq {
 
 constexpr int MERGE_THREADS = 256;
+constexpr int MERGE_WARPS = MERGE_THREADS / 32;
 constexpr int MERGE_CAP_MAX = 8192;  // 64 KB of keys
+constexpr int MERGE_MAX_SETS = 1024;
 
-__device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, int S) {
-    for (int s = 2; s <= S; s <<= 1) {
-        for (int j = s >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (S >> 1); i += MERGE_THREADS) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int hi = lo | j;
-                const bool desc = (lo & s) == 0;
-                const uint64_t a = keys[lo], b = keys[hi];
-                if (desc ? (a < b) : (a > b)) {
-                    keys[lo] = b;
-                    keys[hi] = a;
-                }
-            }
-            __syncthreads();
+// a, b: 128 keys each, sorted descending, 4 per lane (element e = r*32 + lane).  a <- the best 128 of the
+// union, sorted descending.  max(a[e], b[127-e]) is a bitonic sequence holding exactly those 128 keys;
+// one bitonic merge (strides 64, 32 in registers, 16..1 by shuffle) sorts it.
+__device__ __forceinline__ void merge_top128(uint64_t (&a)[4], const uint64_t (&b)[4], int lane) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) a[r] = umax64(a[r], __shfl_sync(VQ_FULL_MASK, b[3 - r], 31 - lane));
+#pragma unroll
+    for (int r = 0; r < 2; r++) {  // stride 64
+        const uint64_t x = a[r], y = a[r + 2];
+        a[r] = umax64(x, y);
+        a[r + 2] = umin64(x, y);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r += 2) {  // stride 32
+        const uint64_t x = a[r], y = a[r + 1];
+        a[r] = umax64(x, y);
+        a[r + 1] = umin64(x, y);
+    }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint64_t other = __shfl_xor_sync(VQ_FULL_MASK, a[r], j);
+            a[r] = lower ? umax64(a[r], other) : umin64(a[r], other);
         }
     }
 }
 
-__device__ __forceinline__ int next_pow2(int x) {
-    int p = 2;
-    while (p < x) p <<= 1;
-    return p;
+// folds `n` keys at keys[0..n) into the warp's running top-128: warp w takes the 256-key chunks w, w+8, ...
+__device__ __forceinline__ void fold_chunks(const uint64_t* keys, int n, uint64_t (&run)[4], int warp, int lane) {
+    for (int c0 = warp * 256; c0 < n; c0 += MERGE_WARPS * 256) {
+        uint64_t ch[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int e = c0 + r * 32 + lane;
+            ch[r] = e < n ? keys[e] : 0ull;
+        }
+        warp_bitonic_sort_desc<8>(ch, lane);
+        const uint64_t top[4] = {ch[0], ch[1], ch[2], ch[3]};
+        merge_top128(run, top, lane);
+    }
 }
 
-// Gathers the (unsorted) candidate lists of one query — the running merged list in set 0 (if
-// use_set0) plus sets [set_begin, set_begin + n_sets) — sorts them in shared memory, and writes the
-// best k back to set 0 (sorted raw pairs + count), the k-th score to thr_out (the primed threshold
-// of the next pass), and, for the last pass, the final (scores, ids).  One CTA per query.
-constexpr int MERGE_MAX_SETS = 1024;
+// 8 per-warp top-128 sets -> warp 0 holds the CTA-wide top-128 (sorted).  wtop: [8][128] keys of shared memory.
+__device__ __forceinline__ void tree_merge(uint64_t* wtop, uint64_t (&run)[4], int warp, int lane) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) wtop[warp * 128 + r * 32 + lane] = run[r];
+    __syncthreads();
+    for (int step = 1; step < MERGE_WARPS; step <<= 1) {
+        if ((warp & (2 * step - 1)) == 0) {
+            uint64_t other[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) other[r] = wtop[(warp + step) * 128 + r * 32 + lane];
+            merge_top128(run, other, lane);
+#pragma unroll
+            for (int r = 0; r < 4; r++) wtop[warp * 128 + r * 32 + lane] = run[r];
+        }
+        __syncthreads();
+    }
+}
 
+// Merge step of one pass, one CTA per query.  Gathers the (unsorted) candidate lists — the running merged list
+// in set 0 (if use_set0) plus sets [set_begin, set_begin + n_sets) — into shared memory; every warp sorts
+// 256-key chunks in registers and keeps a running top-128; a 3-level tree leaves the CTA-wide top-128 in
+// warp 0, which writes the best k back to set 0 (sorted raw pairs + count), the k-th score to thr_out (the
+// primed threshold of the next pass) and, for the last pass, the final (scores, ids).
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int use_set0, int set_begin, int n_sets, int nq_pad, int k,
                    long long id_offset, float* __restrict__ thr_out, float* __restrict__ out_scores, long long* __restrict__ out_ids,
                    int cap) {
-    extern __shared__ uint64_t keys[];
-    __shared__ int off_s[MERGE_MAX_SETS + 2];  // exclusive prefix sums of the list lengths (index 0 = set 0)
+    extern __shared__ uint64_t keys[];           // [cap] gathered keys, then [8][128] for the tree
+    __shared__ int off_s[MERGE_MAX_SETS + 2];     // exclusive prefix sums of the list lengths (index 0 = set 0)
     __shared__ int round_end;
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = n_sets + 1;  // logical list l: 0 = running merged list (set 0), l >= 1 = set_begin + l - 1
-    // all list lengths at once (the loads are independent), then a serial scan in shared memory
     for (int l = threadIdx.x; l < L; l += MERGE_THREADS) {
         const int set = l == 0 ? 0 : set_begin + l - 1;
         off_s[l + 1] = (l == 0 && !use_set0) ? 0 : counts[(size_t)set * nq_pad + q];
@@ -66,88 +104,86 @@ merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int u
         for (int l = 1; l <= L; l++) { run += off_s[l]; off_s[l] = run; }
     }
     __syncthreads();
-    int have = 0, l0 = 0;
-    do {
-        // this round takes lists [l0, l1): as many as fit beside the `have` keys kept from earlier rounds
-        if (threadIdx.x == 0) {
+    const int total = off_s[L];
+    uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
+    int l0 = 0;
+    while (l0 < L) {
+        if (threadIdx.x == 0) {  // this round: as many whole lists as fit in the gather buffer
             int l1 = l0;
-            while (l1 < L && have + (off_s[l1 + 1] - off_s[l0]) <= cap) l1++;
+            while (l1 < L && off_s[l1 + 1] - off_s[l0] <= cap) l1++;
             round_end = l1;
         }
         __syncthreads();
         const int l1 = round_end;
         const int base = off_s[l0];
-        for (int l = l0 + warp; l < l1; l += MERGE_THREADS / 32) {
+        for (int l = l0 + warp; l < l1; l += MERGE_WARPS) {
             const int set = l == 0 ? 0 : set_begin + l - 1;
             const int n = off_s[l + 1] - off_s[l];
             const unsigned long long* src = reinterpret_cast<const unsigned long long*>(lists + ((size_t)set * nq_pad + q) * VQ_CAP);
-            for (int i = lane; i < n; i += 32) keys[have + off_s[l] - base + i] = raw_to_key(__ldcg(src + i));
+            for (int i = lane; i < n; i += 32) keys[off_s[l] - base + i] = raw_to_key(__ldcg(src + i));
         }
-        const int fill = have + off_s[l1] - base;
-        const int S = next_pow2(fill);
-        for (int i = fill + threadIdx.x; i < S; i += MERGE_THREADS) keys[i] = 0ull;
         __syncthreads();
-        block_bitonic_sort_desc(keys, S);
-        have = fill < k ? fill : k;
+        fold_chunks(keys, off_s[l1] - base, run, warp, lane);
+        __syncthreads();
         l0 = l1;
-    } while (l0 < L);
-    uint64_t* dst = lists + (size_t)q * VQ_CAP;  // set 0
-    for (int i = threadIdx.x; i < have; i += MERGE_THREADS) dst[i] = key_to_raw(keys[i]);
-    if (threadIdx.x == 0) {
-        counts[q] = have;
-        if (thr_out) thr_out[q] = have >= k ? key_score(keys[k - 1]) : -FLT_MAX;
     }
-    if (out_scores) {
-        for (int i = threadIdx.x; i < k; i += MERGE_THREADS) {
-            if (i < have) {
-                out_scores[(size_t)q * k + i] = key_score(keys[i]);
-                out_ids[(size_t)q * k + i] = (long long)key_row(keys[i]) + id_offset;
-            } else {
-                out_scores[(size_t)q * k + i] = -FLT_MAX;
-                out_ids[(size_t)q * k + i] = -1;
+    tree_merge(keys, run, warp, lane);
+    if (warp == 0) {
+        const int have = total < k ? total : k;
+        uint64_t* dst = lists + (size_t)q * VQ_CAP;  // set 0
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int e = r * 32 + lane;
+            if (e < have) dst[e] = key_to_raw(run[r]);
+            if (e == k - 1 && thr_out) thr_out[q] = total >= k ? key_score(run[r]) : -FLT_MAX;
+            if (out_scores && e < k) {
+                out_scores[(size_t)q * k + e] = e < have ? key_score(run[r]) : -FLT_MAX;
+                out_ids[(size_t)q * k + e] = e < have ? (long long)key_row(run[r]) + id_offset : -1;
             }
         }
+        if (lane == 0) counts[q] = have;
     }
 }
 
+// Cross-GPU merge: per query, the G per-shard top-k lists [n_lists][nq][k_in] -> global top-k_out.
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, int n_lists, int nq, int k_in, int k_out,
                   float* __restrict__ out_scores, long long* __restrict__ out_ids, int cap) {
     extern __shared__ uint64_t keys[];
     const int q = blockIdx.x;
-    int have = 0, c = 0;
-    do {
-        int fill = have;
-        while (c < n_lists && fill + k_in <= cap) {
-            const size_t base = ((size_t)c * nq + q) * k_in;
-            for (int i = threadIdx.x; i < k_in; i += MERGE_THREADS) {
-                const long long id = ids[base + i];
-                keys[fill + i] = id >= 0 ? make_key(scores[base + i], (uint32_t)id) : 0ull;  // padding sorts last
-            }
-            fill += k_in;
-            c++;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
+    const int per_round = cap / k_in;  // whole lists per gather round (>= 1 by construction of cap)
+    for (int c0 = 0; c0 < n_lists; c0 += per_round) {
+        const int c1 = min(n_lists, c0 + per_round);
+        const int n = (c1 - c0) * k_in;
+        for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
+            const int c = c0 + i / k_in, j = i - (i / k_in) * k_in;
+            const size_t at = ((size_t)c * nq + q) * k_in + j;
+            const long long id = ids[at];
+            keys[i] = id >= 0 ? make_key(scores[at], (uint32_t)id) : 0ull;  // padding sorts last
         }
-        const int S = next_pow2(fill);
-        for (int i = fill + threadIdx.x; i < S; i += MERGE_THREADS) keys[i] = 0ull;
         __syncthreads();
-        block_bitonic_sort_desc(keys, S);
-        have = fill < k_out ? fill : k_out;
-    } while (c < n_lists);
-    for (int i = threadIdx.x; i < k_out; i += MERGE_THREADS) {
-        const uint64_t key = i < have ? keys[i] : 0ull;
-        if (key != 0ull) {
-            out_scores[(size_t)q * k_out + i] = key_score(key);
-            out_ids[(size_t)q * k_out + i] = (long long)key_row(key);
-        } else {
-            out_scores[(size_t)q * k_out + i] = -FLT_MAX;
-            out_ids[(size_t)q * k_out + i] = -1;
+        fold_chunks(keys, n, run, warp, lane);
+        __syncthreads();
+    }
+    tree_merge(keys, run, warp, lane);
+    if (warp == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int e = r * 32 + lane;
+            if (e < k_out) {
+                const bool valid = run[r] != 0ull;
+                out_scores[(size_t)q * k_out + e] = valid ? key_score(run[r]) : -FLT_MAX;
+                out_ids[(size_t)q * k_out + e] = valid ? (long long)key_row(run[r]) : -1;
+            }
         }
     }
 }
 
 static int pick_cap(long long total, int k) {
     long long need = total > 2LL * k ? total : 2LL * k;
-    int cap = 256;
+    int cap = 1024;  // also hosts the [8][128] tree buffer
     while (cap < need && cap < MERGE_CAP_MAX) cap <<= 1;
     return cap;
 }
@@ -174,7 +210,7 @@ int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin
 int merge_topk_launch(const float* scores, const long long* ids, int n_lists, int nq, int k_in, int k_out,
                       float* out_scores, long long* out_ids, cudaStream_t stream) {
     if (nq <= 0) return 0;
-    if (k_in < 1 || k_out < 1 || k_in + k_out > MERGE_CAP_MAX) return -2;
+    if (k_in < 1 || k_out < 1 || k_out > VQ_KMAX || k_in > MERGE_CAP_MAX) return -2;
     const int cap = pick_cap((long long)n_lists * k_in, k_in > k_out ? k_in : k_out);
     const size_t smem = (size_t)cap * sizeof(uint64_t);
     static bool attr_set = false;

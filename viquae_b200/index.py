@@ -142,6 +142,17 @@ class B200FlatIndex(BaseIndex):
         except Exception:
             pass
 
+    # HF datasets deep-copies Dataset._indexes on every formatting/transform call; the index is a handle on
+    # device memory, so copies share it (copying 18 GB of HBM per `with_format` is never what the caller wants)
+    def __deepcopy__(self, memo):
+        return self
+
+    def __copy__(self):
+        return self
+
+    def __reduce__(self):
+        raise TypeError("B200FlatIndex holds device memory and cannot be pickled: use save()/load()")
+
     def set_variant(self, variant: Optional[str]):
         if variant not in _VARIANTS:
             raise ValueError(f"variant must be one of {list(_VARIANTS)}")
