@@ -107,6 +107,16 @@ int vq_prep_rows(const void* src, int src_dtype, void* dst, int dst_dtype, uint6
 int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out, float* out_scores,
                   int64_t* out_ids, void* stream);
 
+/* Searcher.__call__'s per-hit post-processing (meerqat/ir/search.py:413-440) for one index and one query
+ * batch: article -> passage expansion through a CSR mapping (map_offsets int64 [n_rows+1], map_targets int64
+ * [nnz]; both NULL = identity), many2one (0 = overwrite like a dict, 1 = 'max'), stop after the hit that
+ * brings the run to >= k documents.  Device pointers.  scores f32 / ids i64 [nq, k_in] as returned by
+ * vq_index_search.  Outputs in dict INSERTION order: out_ids i64 / out_scores f64 [nq, out_cap] (-1 padding),
+ * out_counts i32 [nq]; out_cap must be >= k + (largest fan-out of the mapping) - 1, else *overflow_flag = 1. */
+int vq_expand_hits(const float* scores, const int64_t* ids, int nq, int k_in, const int64_t* map_offsets, const int64_t* map_targets,
+                   int many2one_max, int k, int out_cap, double* out_scores, int64_t* out_ids, int32_t* out_counts, int32_t* overflow_flag,
+                   void* stream);
+
 /* meerqat.ir.fuse: default_minimum (fuse.py:132-149) -> normalisation (gzmuv fuse.py:86-129; ranx
  * zmuv / min-max) -> ranx wsum -> descending sort, for n_runs dense runs of one query batch.
  * Device pointers.  scores float64 / ids int64 [n_runs, nq, k_in] (id < 0 = absent entry);

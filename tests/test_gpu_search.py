@@ -275,3 +275,37 @@ def test_hf_dataset_dispatch_and_dataset_search_with_fusion(tmp_path):
     for qid in ("q0", "q7", "q39"):
         assert set(fused[qid]) == set(ref[qid])
         assert np.allclose([fused[qid][d_] for d_ in ref[qid]], list(ref[qid].values()), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("many2one", [None, "max"])
+def test_gpu_postprocessing_equals_reference_loop(many2one):
+    """K6 (vq_expand_hits) vs the Python restatement of Searcher.__call__'s loop (search.py:413-440), including
+    overlapping mappings (dict overwrite / max semantics), early stop at k and padded hits."""
+    from viquae_b200.postprocess import CSRMapping, expand_hits
+    from viquae_b200.search import Searcher
+    rng = np.random.default_rng(2)
+    n_rows, nq, k = 500, 64, 20
+    mapping = {r: sorted(rng.choice(300, size=int(rng.integers(0, 6)), replace=False).tolist()) for r in range(n_rows)}
+    scores = np.sort(rng.normal(70, 2, size=(nq, k)).astype(np.float32), axis=1)[:, ::-1].copy()
+    ids = np.stack([rng.choice(n_rows, size=k, replace=False) for _ in range(nq)]).astype(np.int64)
+    ids[5, 7:] = -1  # a row with fewer than k hits
+    scores[5, 7:] = np.finfo(np.float32).min
+
+    class KB:
+        index_mapping = mapping
+    KB.many2one = many2one
+    s = Searcher.__new__(Searcher)
+    s.k = k
+    out_s, out_i, out_c = expand_hits(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda(), CSRMapping(mapping, n_rows=n_rows), many2one, k)
+    out_s, out_i, out_c = out_s.cpu().numpy(), out_i.cpu().numpy(), out_c.cpu().numpy()
+    for q in range(nq):
+        ref = {}
+        valid = ids[q] >= 0
+        s._record(KB, ref, scores[q][valid], ids[q][valid])
+        n = out_c[q]
+        assert [str(d) for d in out_i[q, :n]] == list(ref), q          # same documents in the same (insertion) order
+        assert np.array_equal(out_s[q, :n].astype(np.float32), np.array(list(ref.values()), dtype=np.float32))
+        assert (out_i[q, n:] == -1).all()
+    # identity mapping: the run is the hit list
+    out_s, out_i, out_c = expand_hits(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda(), None, None, k)
+    assert np.array_equal(out_i.cpu().numpy()[0], ids[0]) and out_c.cpu().numpy()[5] == 7

@@ -464,6 +464,19 @@ int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, 
     return VQ_OK;
 }
 
+int vq_expand_hits(const float* scores, const int64_t* ids, int nq, int k_in, const int64_t* map_offsets, const int64_t* map_targets,
+                   int many2one_max, int k, int out_cap, double* out_scores, int64_t* out_ids, int32_t* out_counts, int32_t* overflow_flag,
+                   void* stream) {
+    if (!scores || !ids || !out_scores || !out_ids || !out_counts || !overflow_flag || nq < 0 || k_in < 1 || k < 1 || out_cap < 1)
+        return fail(VQ_ERR_INVALID, "vq_expand_hits: bad arguments");
+    if ((map_offsets == nullptr) != (map_targets == nullptr)) return fail(VQ_ERR_INVALID, "vq_expand_hits: offsets and targets go together");
+    int rc = vq::expand_hits_launch(scores, (const long long*)ids, nq, k_in, (const long long*)map_offsets, (const long long*)map_targets,
+                                    many2one_max, k, out_cap, out_scores, (long long*)out_ids, out_counts, overflow_flag, (cudaStream_t)stream);
+    if (rc == -2) return fail(VQ_ERR_UNSUPPORTED, "vq_expand_hits: out_cap=%d too large for shared memory", out_cap);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_expand_hits: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
 size_t vq_fuse_workspace_bytes(int n_runs, int nq, int k_in) {
     if (n_runs < 1 || nq < 1 || k_in < 1) return 0;
     return vq::fuse_workspace_bytes(n_runs, nq, k_in);

@@ -75,6 +75,11 @@ int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin
 int merge_topk_launch(const float* scores, const long long* ids, int n_lists, int nq, int k_in, int k_out,
                       float* out_scores, long long* out_ids, cudaStream_t stream);
 
+// ---- K6: run post-processing (vq_post.cu)
+int expand_hits_launch(const float* scores, const long long* ids, int nq, int k_in, const long long* map_offsets,
+                       const long long* map_targets, int many2one_max, int k, int out_cap, double* out_scores, long long* out_ids,
+                       int* out_counts, int* overflow, cudaStream_t stream);
+
 // ---- K5: score fusion (vq_fuse.cu)
 struct FuseParams {
     int n_runs, nq, k_in, u_max;

@@ -26,6 +26,7 @@ import numpy as np
 from . import _lib
 from .fuse import Fusion
 from .index import B200FlatIndex, METRIC_INNER_PRODUCT, parse_string_factory
+from .postprocess import CSRMapping, expand_hits
 from .runs import Qrels, Run, evaluate
 
 LEGACY_KEYS = ("es", "kind_str", "normalization", "interpolation_weight")  # older config dialect
@@ -159,6 +160,16 @@ class KnowledgeBase:
             self.dataset._indexes[index_name] = engine
         return do_L2norm
 
+    def csr_mapping(self, device: int = 0):
+        """The article -> passages mapping as device CSR arrays (built once per device); None without a mapping."""
+        if self.index_mapping is None:
+            return None
+        cache = self.__dict__.setdefault("_csr", {})
+        if device not in cache:
+            n_rows = max([max(self.index_mapping) + 1 if self.index_mapping else 0] + [len(e) for e in self._engines.values()])
+            cache[device] = CSRMapping(self.index_mapping, n_rows=n_rows, device=device)
+        return cache[device]
+
     # ------------------------------------------------------------------ search
     def search_batch(self, index_name, queries, k=100):
         """``(scores, indices)`` of the k best KB rows per query (search.py:135-146): float32 [nq, k] descending,
@@ -192,8 +203,10 @@ class Searcher:
     (meerqat/ir/search.py:296-459)."""
 
     def __init__(self, kb_kwargs, k=100, reference_kb_path=None, reference_key="passage", qrels=None, request_timeout=1000,
-                 es_client_kwargs={}, fusion_kwargs={}, metrics_kwargs={}, do_fusion=None, qnonrels=None, find_relevant=None):
+                 es_client_kwargs={}, fusion_kwargs={}, metrics_kwargs={}, do_fusion=None, qnonrels=None, find_relevant=None,
+                 gpu_postprocess=True):
         self.k = k
+        self.gpu_postprocess = gpu_postprocess
         self.kbs = {}
         self.qrels = {}
         if qrels is not None:
@@ -256,6 +269,36 @@ class Searcher:
             if len(run_q) >= self.k:
                 break
 
+    def _search_index(self, kb, index_name, index, batch):
+        """One index, one batch -> fills self.runs[index_name].  Device path: search -> K6 expansion -> one D2H
+        copy; `None` queries (search.py:148-171) simply get an empty run."""
+        import torch
+
+        queries = batch[index.key]
+        run = self.runs[index_name]
+        kept = [i for i, query in enumerate(queries) if query is not None]
+        for q_id in batch["id"]:
+            run.setdefault(q_id, {})
+        if not kept:
+            return
+        engine = kb._engines[index_name]
+        fresh = all(len(run[batch["id"][i]]) == 0 for i in kept)
+        if not (getattr(self, "gpu_postprocess", True) and fresh):
+            scores, indices = kb.search_batch(index_name, [queries[i] for i in kept], k=self.k)
+            for j, i in enumerate(kept):
+                self._record(kb, run[batch["id"][i]], scores[j], indices[j])
+            return
+        q = np.array([queries[i] for i in kept], dtype=np.float32)
+        if q.ndim != 2:
+            raise ValueError("Shape of query must be 2D")
+        dev = torch.device(f"cuda:{engine.device}")
+        s, ids = engine.search_tensors(torch.from_numpy(q).to(dev), self.k)
+        out_s, out_i, out_c = expand_hits(s, ids, kb.csr_mapping(engine.device), kb.many2one, self.k)
+        out_s, out_i, out_c = out_s.cpu().numpy(), out_i.cpu().numpy(), out_c.cpu().numpy()
+        for j, i in enumerate(kept):
+            n = int(out_c[j])
+            run[batch["id"][i]].update({str(int(d)): float(v) for d, v in zip(out_i[j, :n], out_s[j, :n])})
+
     def __call__(self, batch):
         """Search a batch with every index of every KB; ``batch`` is an HF batch dict with ``id``, the query
         columns named by each index's ``key`` and (only with ``find_relevant``) ``output``."""
@@ -263,22 +306,18 @@ class Searcher:
         outputs = batch.get("output", [None] * n)
         for kb in self.kbs.values():
             for index_name, index in kb.indexes.items():
-                queries = batch[index.key]
-                if any(query is None for query in queries):
-                    scores_batch, indices_batch = kb.search_batch_if_not_None(index_name, queries, k=self.k)
-                else:
-                    scores_batch, indices_batch = kb.search_batch(index_name, queries, k=self.k)
-                for q_id, scores, indices, gt in zip(batch["id"], scores_batch, indices_batch, outputs):
-                    run_q = self.runs[index_name].setdefault(q_id, {})
-                    self._record(kb, run_q, scores, indices)
-                    if self.reference_kb is not None:
-                        self.qrels.setdefault(q_id, {})
-                        self.qnonrels.setdefault(q_id, {})
-                        retrieved = run_q.keys() - (self.qrels[q_id].keys() | self.qnonrels[q_id].keys())
-                        _, relevant = self.find_relevant(retrieved, gt["original_answer"], gt["answer"], self.reference_kb,
-                                                         reference_key=self.reference_key)
-                        self.qrels[q_id].update({str(i): 1 for i in relevant})
-                        self.qnonrels[q_id].update({i: 0 for i in retrieved - self.qrels[q_id].keys()})
+                self._search_index(kb, index_name, index, batch)
+                if self.reference_kb is None:
+                    continue
+                for q_id, gt in zip(batch["id"], outputs):
+                    run_q = self.runs[index_name][q_id]
+                    self.qrels.setdefault(q_id, {})
+                    self.qnonrels.setdefault(q_id, {})
+                    retrieved = run_q.keys() - (self.qrels[q_id].keys() | self.qnonrels[q_id].keys())
+                    _, relevant = self.find_relevant(retrieved, gt["original_answer"], gt["answer"], self.reference_kb,
+                                                     reference_key=self.reference_key)
+                    self.qrels[q_id].update({str(i): 1 for i in relevant})
+                    self.qnonrels[q_id].update({i: 0 for i in retrieved - self.qrels[q_id].keys()})
         return batch
 
 
