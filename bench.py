@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--variant", default=None, choices=[None, "auto", "tc_cg1", "tc_cg2", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-calls", type=int, default=0, help="also time this many single calls end to end (p50/p99, BASELINE config 5)")
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="corpus rows of the CPU sample (default: 1.5M inline, 3M for --impl reference)")
     return ap.parse_args()
 
@@ -269,6 +270,21 @@ def run_ours(args):
     # ---- end to end through the host-buffer API
     e2e_ms, _, _ = timed(step_e2e, args.steps, args.warmup)
 
+    latency = None
+    if args.latency_calls > 0:
+        # per-call latency through the host-buffer API (what interact/system.py's one-question loop would see)
+        lat = []
+        for _ in range(50):
+            step_e2e()
+        for _ in range(args.latency_calls):
+            barrier()
+            t_a = time.perf_counter()
+            step_e2e()
+            lat.append((time.perf_counter() - t_a) * 1e6)
+        lat.sort()
+        latency = {"calls": len(lat), "p50_us": lat[len(lat) // 2], "p99_us": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
+                   "min_us": lat[0], "what": "wall clock around one host-buffer search call (H2D + search + merge + D2H + sync)"}
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = args.nq / (ms_per_step / 1e3)
@@ -325,6 +341,8 @@ def run_ours(args):
             "gpu_launches": launches_timed,
             "roofline": roof,
         }
+        if latency is not None:
+            line["latency"] = latency
         if world == 1 and not args.no_cpu_baseline:
             try:
                 times, scale, cores, sample_rows = cpu_port_sample(args, device, args.cpu_sample_rows or 1_500_000, repeats=1, warmup=0)

@@ -273,7 +273,7 @@ struct SearchPlan {
     int n_passes;
     int tile_b[VQ_MAX_PASSES + 1];
     vq::TcPlan tc[VQ_MAX_PASSES];
-    vq::F32Plan f32;
+    vq::F32Plan f32[VQ_MAX_PASSES];
     vq::StreamPlan st;
     int pass_sets;  // largest number of candidate-list sets any pass writes (set 0 is the running merge)
     int nq_pad;
@@ -285,9 +285,27 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     sp->n_passes = 1;
     if (idx->dtype == VQ_F32) {
         sp->kind = 0;
-        vq::f32_plan(nq, n, idx->n_sms, &sp->f32);
-        sp->pass_sets = sp->f32.n_chunks;
-        sp->nq_pad = sp->f32.nq_pad;
+        // same threshold-priming schedule as the tensor-core path (see below), in tiles of 128 rows
+        const int n_tiles = (int)((n + 127) / 128);
+        const int m_tiles = (nq + 127) / 128;
+        int first = (idx->n_sms * 2) / m_tiles;
+        if (first < 1) first = 1;
+        if (first > 56) first = 56;
+        int np = 0;
+        sp->tile_b[0] = 0;
+        long long b = first;
+        while (np < VQ_MAX_PASSES - 1 && b * 4 < n_tiles) {
+            sp->tile_b[++np] = (int)b;
+            b *= 16;
+        }
+        sp->tile_b[++np] = n_tiles;
+        sp->n_passes = np;
+        sp->pass_sets = 0;
+        for (int p = 0; p < np; p++) {
+            vq::f32_plan(nq, (long long)(sp->tile_b[p + 1] - sp->tile_b[p]) * 128, idx->n_sms, &sp->f32[p]);
+            if (sp->f32[p].n_chunks > sp->pass_sets) sp->pass_sets = sp->f32[p].n_chunks;
+        }
+        sp->nq_pad = sp->f32[0].nq_pad;
     } else {
         int variant = idx->variant;
         if (variant == VQ_VARIANT_AUTO) variant = (nq <= 128) ? VQ_VARIANT_TC_CG1 : VQ_VARIANT_TC_CG2;
@@ -392,13 +410,22 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
                                             last ? out_scores : nullptr, last ? (long long*)out_ids : nullptr, expected, s);
             idx->launches += 2;
         }
+    } else if (sp.kind == 0) {
+        for (int p = 0; p < sp.n_passes && !rc; p++) {
+            const bool last = p == sp.n_passes - 1;
+            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 128;
+            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, rows_end, idx->ld, idx->d, k, sp.f32[p],
+                                     sp.tile_b[p], sp.tile_b[p + 1], p ? thr : nullptr, lists + (size_t)sp.nq_pad * VQ_CAP,
+                                     counts + sp.nq_pad, s);
+            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 128 + k : 4096;
+            if (!rc)
+                rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.f32[p].n_chunks, sp.nq_pad, nq, k, idx->id_offset, last ? nullptr : thr,
+                                            last ? out_scores : nullptr, last ? (long long*)out_ids : nullptr, expected, s);
+            idx->launches += 2;
+        }
     } else {
-        if (sp.kind == 0)
-            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, ntot, idx->ld, idx->d, k, sp.f32,
-                                     lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
-        else
-            rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.st,
-                                        lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
+        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.st,
+                                    lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
         if (!rc)
             rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, idx->id_offset, nullptr, out_scores,
                                         (long long*)out_ids, sp.pass_sets * k, s);

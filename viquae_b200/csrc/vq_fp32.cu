@@ -19,8 +19,8 @@ constexpr int LDS = BM + 4;  // padded row of the k-major smem tiles
 
 __global__ void __launch_bounds__(THREADS, 2)
 f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __restrict__ X, long long n_rows, int ld_x, int d, int k,
-                int m_tiles, int n_tiles, int n_chunks, int tiles_per_chunk, int nq_pad, uint64_t* __restrict__ lists,
-                int* __restrict__ counts) {
+                int m_tiles, int tile_begin, int n_tiles, int n_chunks, int tiles_per_chunk, int nq_pad, const float* __restrict__ init_thr,
+                uint64_t* __restrict__ lists, int* __restrict__ counts) {
     __shared__ float As[BK][LDS];
     __shared__ float Bs[BK][LDS];
     __shared__ float thr_s[BM];
@@ -40,10 +40,11 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
         uint64_t* item_lists = lists + ((size_t)chunk * nq_pad + q0) * VQ_CAP;
         if (tid < BM) {
             cnt_s[tid] = 0;
-            thr_s[tid] = (q0 + tid < nq) ? -FLT_MAX : INFINITY;
+            // primed threshold (k-th score of the rows of earlier passes, all with lower ids) or -FLT_MAX
+            thr_s[tid] = (q0 + tid < nq) ? (init_thr ? init_thr[q0 + tid] : -FLT_MAX) : INFINITY;
         }
         __syncthreads();
-        const int t0 = chunk * tiles_per_chunk;
+        const int t0 = tile_begin + chunk * tiles_per_chunk;
         const int t1 = min(n_tiles, t0 + tiles_per_chunk);
         for (int t = t0; t < t1; t++) {
             const long long x0 = (long long)t * BN;
@@ -139,18 +140,15 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
                     const int m = warp_prune_list(item_lists + (size_t)r * VQ_CAP, n, k, lane, thr_new);
                     if (lane == 0) {
                         cnt_s[r] = m;
-                        thr_s[r] = thr_new;
+                        thr_s[r] = fmaxf(thr_s[r], thr_new);  // never loosen a primed threshold
                     }
                 }
             }
             // (the __syncthreads at the top of the next K loop / below orders these writes)
         }
         __syncthreads();
-        for (int r = warp; r < BM; r += THREADS / 32) {
-            float thr_new;
-            const int m = warp_prune_list(item_lists + (size_t)r * VQ_CAP, cnt_s[r], k, lane, thr_new);
-            if (lane == 0) counts[(size_t)chunk * nq_pad + q0 + r] = (q0 + r < nq) ? m : 0;
-        }
+        // publish the (unsorted) list lengths; the pass's merge kernel sorts
+        if (tid < BM) counts[(size_t)chunk * nq_pad + q0 + tid] = (q0 + tid < nq) ? cnt_s[tid] : 0;
         __syncthreads();
     }
 }
@@ -186,11 +184,12 @@ void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan) {
 }
 
 int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
-                    const F32Plan& plan, uint64_t* lists, int* counts, cudaStream_t stream) {
+                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, uint64_t* lists, int* counts,
+                    cudaStream_t stream) {
     if (k < 1 || k > VQ_KMAX) return -2;
     if (nq <= 0) return 0;
-    f32::f32_topk_kernel<<<plan.n_ctas, f32::THREADS, 0, stream>>>(q, nq, ld_q, x, n_rows, ld_x, d, k, plan.m_tiles, plan.n_tiles,
-                                                                  plan.n_chunks, plan.tiles_per_chunk, plan.nq_pad, lists, counts);
+    f32::f32_topk_kernel<<<plan.n_ctas, f32::THREADS, 0, stream>>>(q, nq, ld_q, x, n_rows, ld_x, d, k, plan.m_tiles, tile_begin, tile_end,
+                                                                  plan.n_chunks, plan.tiles_per_chunk, plan.nq_pad, init_thr, lists, counts);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -52,8 +52,10 @@ struct F32Plan {
     int m_tiles, n_tiles, n_chunks, tiles_per_chunk, nq_pad, n_ctas;
 };
 void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan);
+// one pass over corpus tiles (128 rows each) [tile_begin, tile_end); plan from f32_plan(nq, (tile_end - tile_begin) * 128 rows)
 int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
-                    const F32Plan& plan, uint64_t* lists, int* counts, cudaStream_t stream);
+                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, uint64_t* lists, int* counts,
+                    cudaStream_t stream);
 
 // ---- K2: small-batch HBM-streaming contraction + fused top-k (vq_stream.cu)
 struct StreamPlan {

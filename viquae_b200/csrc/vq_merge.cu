@@ -195,7 +195,10 @@ int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin
     // capacity: at least one full list + the running top-k must fit
     const int cap = pick_cap(expected_total, VQ_CAP);
     const size_t smem = (size_t)cap * sizeof(uint64_t);
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& attr_set = attr_set_dev[dev_ & 63];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP_MAX * 8);
         if (e != cudaSuccess) return -(int)e;
@@ -213,7 +216,10 @@ int merge_topk_launch(const float* scores, const long long* ids, int n_lists, in
     if (k_in < 1 || k_out < 1 || k_out > VQ_KMAX || k_in > MERGE_CAP_MAX) return -2;
     const int cap = pick_cap((long long)n_lists * k_in, k_in > k_out ? k_in : k_out);
     const size_t smem = (size_t)cap * sizeof(uint64_t);
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& attr_set = attr_set_dev[dev_ & 63];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP_MAX * 8);
         if (e != cudaSuccess) return -(int)e;

@@ -81,8 +81,11 @@ int expand_hits_launch(const float* scores, const long long* ids, int nq, int k_
     if (nq <= 0) return 0;
     const size_t smem = (size_t)POST_WARPS * out_cap * (sizeof(long long) + sizeof(float));
     if (smem > 200 * 1024) return -2;
-    static size_t attr_set = 48 * 1024;
-    if (smem > attr_set) {
+    static size_t attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    size_t& attr_set = attr_set_dev[dev_ & 63];
+    if (smem > attr_set && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(expand_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return -(int)e;
         attr_set = smem;

@@ -151,8 +151,11 @@ static int launch(const void* q16, int nq, int ld_q, const void* x16, long long 
     const int num_kb = (ld_x + KB - 1) / KB;
     const size_t smem = (size_t)num_kb * NT * 64 * sizeof(uint4);
     if (smem > 200 * 1024) return -2;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
+    static size_t attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    size_t& attr_set = attr_set_dev[dev_ & 63];
+    if (smem > attr_set && smem > 0) {
         cudaError_t e = cudaFuncSetAttribute(stream_topk_kernel<NT, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return -(int)e;
         attr_set = smem;

@@ -415,7 +415,10 @@ static int encode_2d(CUtensorMap* m, const void* base, int dtype, uint64_t rows,
 template <int CG>
 static int launch_cg(const CUtensorMap& tq, const CUtensorMap& tx, const TcParams& p, int n_clusters, cudaStream_t stream) {
     using C = Cfg<CG>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& attr_set = attr_set_dev[dev_ & 63];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_topk_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (e != cudaSuccess) return -(int)e;
