@@ -80,3 +80,18 @@ def test_l2norm_host_api():
     x = np.array([[3, 4, 0], [0, 0, 0]], np.float32)
     out = L2norm(x)
     assert np.allclose(out[0], [0.6, 0.8, 0]) and np.isnan(out[1]).all()
+
+
+def test_fit_dense_metric_equals_host_metric(golden_dir):
+    """The on-device metric used by Fusion.fit's grid search equals the dict-based evaluate() on the same fused run."""
+    from viquae_b200 import fuse, runs
+    g = json.load(open(os.path.join(golden_dir, "fusion_golden.json")))
+    rr = [fuse.Run(r) for r in g["runs"]]
+    qrels = runs.Qrels({q: {d: 1 for d in list(res)[2:4]} for q, res in g["runs"][0].items()})
+    f = fuse.Fusion(qrels=qrels, runs=rr, norm="zmuv", defmin=True)
+    res = f.fit("mrr@100")
+    (params, score), = res.values()
+    host = runs.evaluate(qrels, f._fused(params["weights"], "zmuv"), "mrr@100")
+    assert abs(host - score) < 1e-12
+    best_host = max(runs.evaluate(qrels, f._fused(w, "zmuv"), "mrr@100") for w in fuse.weight_grid(3))
+    assert abs(best_host - score) < 1e-12

@@ -309,3 +309,38 @@ def test_gpu_postprocessing_equals_reference_loop(many2one):
     # identity mapping: the run is the hit list
     out_s, out_i, out_c = expand_hits(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda(), None, None, k)
     assert np.array_equal(out_i.cpu().numpy()[0], ids[0]) and out_c.cpu().numpy()[5] == 7
+
+
+def test_full_size_corpus_properties():
+    """BASELINE configs[1] at full size (12M x 768 bf16 on one GPU, generated on the device): the oracle cannot
+    run here, so size-independent properties: recomputed scores, ordering, determinism, sharding invariance
+    against two 6M-row halves merged by K4, and agreement between the 256-query and 1-query schedules."""
+    from viquae_b200.index import B200FlatIndex, merge_topk
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs > 60 GB of HBM")
+    N, d, nq, k, chunk = 12_000_000, 768, 256, 100, 1_000_000
+    idx = B200FlatIndex(d=d, dtype="bf16", capacity=N)
+    halves = [B200FlatIndex(d=d, dtype="bf16", capacity=N // 2, id_offset=0), B200FlatIndex(d=d, dtype="bf16", capacity=N // 2, id_offset=N // 2)]
+    for c in range(N // chunk):
+        g = torch.Generator(device="cuda"); g.manual_seed(20240117 + c)
+        x = torch.randn((chunk, d), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16)
+        idx.add(x)
+        halves[0 if c < 6 else 1].add(x)
+        if c == 7:
+            keep = x[:1000].clone()   # rows 7,000,000 .. 7,000,999 for the recomputation check
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    Q = torch.randn((nq, d), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16)
+    Q[:8] = keep[:8] * 4   # plant queries whose best match is a known row
+    s, i = idx.search_tensors(Q, k)
+    assert (i[:8, 0] == torch.arange(7_000_000, 7_000_008, device="cuda")).all()
+    assert torch.allclose(s[:8, 0], (keep[:8].float() * Q[:8].float()).sum(-1), rtol=2e-3)
+    assert (i >= 0).all() and (i < N).all() and (s[:, 1:] <= s[:, :-1]).all()
+    s2, i2 = idx.search_tensors(Q, k)
+    assert torch.equal(i, i2) and torch.equal(s, s2)
+    parts = [h.search_tensors(Q, k) for h in halves]
+    s_m, i_m = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    cmp = flat_ip.compare_results(s.cpu().numpy(), i.cpu().numpy(), s_m.cpu().numpy(), i_m.cpu().numpy(), rel_tol=1e-4)
+    assert cmp["real_mismatches"] == 0 and cmp["overlap"] >= 0.9999, cmp
+    s1, i1 = idx.search_tensors(Q[:1], k)
+    cmp = flat_ip.compare_results(s[:1].cpu().numpy(), i[:1].cpu().numpy(), s1.cpu().numpy(), i1.cpu().numpy(), rel_tol=1e-4)
+    assert cmp["real_mismatches"] == 0, cmp

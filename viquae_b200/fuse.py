@@ -189,21 +189,63 @@ class Fusion:
         # defmin precedes normalisation (fuse.py:183-184 vs :199-200,224-225): the kernel applies them in that order
         return _fuse_runs(self.runs, weights, norm=norm, defmin=self.defmin, name="fusion", device=self.device)
 
+    def _dense_metric(self, dense, rel, out_i, out_c, metric):
+        """mrr@k / precision@k / hit_rate@k / recall@k of a fused dense ranking, on the device (evaluation only:
+        the grid search of fit() calls it once per weight combination).  rel: [nq, max_rel] relevant doc codes, -2 pad."""
+        import torch
+
+        name, _, cut = metric.partition("@")
+        kk = int(cut) if cut else out_i.shape[1]
+        ranked = out_i[:, :kk]
+        hit = (ranked[:, :, None] == rel[:, None, :]).any(-1) & (torch.arange(ranked.shape[1], device=ranked.device)[None, :] < out_c[:, None])
+        judged = (rel >= 0).any(-1)  # queries that have qrels (ranx averages over the qrels' queries)
+        n_judged = int(self._n_qrels_queries)
+        if name == "mrr":
+            first = torch.where(hit.any(-1), hit.float().argmax(-1), torch.full_like(out_c, -1, dtype=torch.int64))
+            v = torch.where(first >= 0, 1.0 / (first.double() + 1.0), torch.zeros_like(first, dtype=torch.float64))
+        elif name == "precision":
+            v = hit.sum(-1).double() / float(kk)
+        elif name == "hit_rate":
+            v = hit.any(-1).double()
+        elif name == "recall":
+            v = hit.sum(-1).double() / (rel >= 0).sum(-1).clamp(min=1).double()
+        else:
+            raise ValueError(f"unsupported metric {metric!r}")
+        return float((v * judged).sum().item()) / max(n_judged, 1)
+
     def fit(self, metric: str = "mrr@100"):
-        """Finds the best weights on the 0.1 grid for every (norm, method); writes ``{norm}_{method}_best_params.yaml``."""
+        """Finds the best weights on the 0.1 grid for every (norm, method); writes ``{norm}_{method}_best_params.yaml``.
+        The runs are converted to dense arrays once; every grid point is one ``vq_fuse`` call + an on-device metric."""
+        import torch
+
         if self.qrels is None:
             raise ValueError("Fusion.fit needs qrels")
         norms = [self.norm] if self.norm is None or isinstance(self.norm, str) else self.norm
         methods = [self.method] if self.method is None or isinstance(self.method, str) else self.method
+        dense = DenseRuns(self.runs)
+        dev = torch.device(f"cuda:{self.device}")
+        d_scores = torch.from_numpy(dense.scores).to(dev)
+        d_ids = torch.from_numpy(dense.ids).to(dev)
+        qrels = self.qrels.qrels
+        self._n_qrels_queries = len(qrels)
+        max_rel = max([sum(1 for g in rels.values() if g > 0) for rels in qrels.values()] + [1])
+        rel = np.full((len(dense.q_ids), max_rel), -2, dtype=np.int64)
+        for qi, q in enumerate(dense.q_ids):
+            codes = [dense._encode[d] for d, g in qrels.get(q, {}).items() if g > 0 and d in dense._encode]
+            rel[qi, :len(codes)] = codes
+            if q in qrels and not codes:
+                rel[qi, 0] = 2 ** 62  # judged query whose relevant documents were never retrieved: counts as 0
+        rel = torch.from_numpy(rel).to(dev)
         results = {}
         for norm in norms:
             for method in methods:
                 self._check_method(method)
                 best, best_score, report = None, -1.0, []
                 for weights in weight_grid(len(self.runs)):
-                    score = evaluate(self.qrels, self._fused(weights, norm), metric)
+                    _, out_i, out_c = fuse_dense(d_scores, d_ids, weights, norm=norm, defmin=self.defmin, device=self.device)
+                    score = self._dense_metric(dense, rel, out_i, out_c.long(), metric)
                     report.append((weights, score))
-                    if score > best_score:  # first best wins, like ranx
+                    if score > best_score + 1e-15:  # first best wins, like ranx
                         best, best_score = weights, score
                 best_params = {"weights": [round(w, 10) for w in best]}
                 results[(norm, method)] = (best_params, best_score)
