@@ -7,7 +7,7 @@
 // (and those follow the same lower-id-first rule).
 //
 // 128 (queries) x 128 (corpus rows) tile per CTA, 256 threads, 8x8 outputs per thread, K staged
-// through shared memory 16 columns at a time (register double buffering).  FFMA-bound.
+// through double-buffered shared memory 16 columns at a time (one barrier per K block).  FFMA-bound.
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
@@ -21,13 +21,15 @@ __global__ void __launch_bounds__(THREADS, 2)
 f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __restrict__ X, long long n_rows, int ld_x, int d, int k,
                 int m_tiles, int tile_begin, int n_tiles, int n_chunks, int tiles_per_chunk, int nq_pad, const float* __restrict__ init_thr,
                 uint64_t* __restrict__ lists, int* __restrict__ counts) {
-    __shared__ float As[BK][LDS];
-    __shared__ float Bs[BK][LDS];
+    __shared__ __align__(16) float As[2][BK][LDS];  // double-buffered k-major tiles
+    __shared__ __align__(16) float Bs[2][BK][LDS];
     __shared__ float thr_s[BM];
     __shared__ int cnt_s[BM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, 8 x 8 outputs each
+    // 16 x 16 threads, 8 x 8 outputs each as 2 x 2 blocks of 4 x 4: rows {4ty..4ty+3, 64+4ty..}, cols {4tx.., 64+4tx..}
+    // (16-byte-strided float4 reads of the B tile are bank-conflict free; the A reads are warp broadcasts)
+    const int ty = tid >> 4, tx = tid & 15;
     // global -> smem staging: thread loads float4 (4 consecutive k) of row lr for A and B, twice (rows lr, lr+64)
     const int lr = tid >> 2, lk = (tid & 3) * 4;
     const int n_items = m_tiles * n_chunks;
@@ -86,27 +88,27 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
                     rb[h] = b;
                 }
             };
-            auto sstore = [&]() {
+            auto sstore = [&](int buf) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int r = lr + h * 64;
-                    As[lk + 0][r] = ra[h].x; As[lk + 1][r] = ra[h].y; As[lk + 2][r] = ra[h].z; As[lk + 3][r] = ra[h].w;
-                    Bs[lk + 0][r] = rb[h].x; Bs[lk + 1][r] = rb[h].y; Bs[lk + 2][r] = rb[h].z; Bs[lk + 3][r] = rb[h].w;
+                    As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y; As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+                    Bs[buf][lk + 0][r] = rb[h].x; Bs[buf][lk + 1][r] = rb[h].y; Bs[buf][lk + 2][r] = rb[h].z; Bs[buf][lk + 3][r] = rb[h].w;
                 }
             };
             gload(0);
+            sstore(0);
+            __syncthreads();
             for (int kb = 0; kb < num_kb; kb++) {
-                __syncthreads();  // previous tile's readers are done with As/Bs
-                sstore();
-                __syncthreads();
-                if (kb + 1 < num_kb) gload(kb + 1);  // overlaps the FFMA block below
+                const int buf = kb & 1;
+                if (kb + 1 < num_kb) gload(kb + 1);  // global loads fly over the FFMA block below
 #pragma unroll
                 for (int kk = 0; kk < BK; kk++) {
                     float a[8], b[8];
-                    const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
-                    const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-                    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+                    const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+                    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
                     a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
                     b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
@@ -114,16 +116,19 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
 #pragma unroll
                         for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
                 }
+                // the other buffer was last read one iteration ago, before the barrier below: safe to overwrite
+                if (kb + 1 < num_kb) sstore(buf ^ 1);
+                __syncthreads();
             }
             // ---- fused top-k: threshold filter -> per-query candidate lists
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int r = ty * 8 + i;
+                const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
                 const float thr = thr_s[r];
                 unsigned long long* list = reinterpret_cast<unsigned long long*>(item_lists + (size_t)r * VQ_CAP);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const long long xr = x0 + tx * 8 + j;
+                    const long long xr = x0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
                     const float s = acc[i][j];
                     if (xr < n_rows && s > thr) {
                         const int pos = atomicAdd(&cnt_s[r], 1);
