@@ -73,6 +73,8 @@ def test_fp32_mode_is_bit_exact(N, nq, d, k):
     ("stream", 20000, 20, 768, 100, "bf16"),
     ("stream", 5000, 32, 512, 10, "f16"),
     (None, 40000, 256, 768, 100, "bf16"),            # the reference's call granularity: 256 queries per call
+    (None, 30000, 140, 2048, 100, "bf16"),           # imagenet-RN50 dimension (config_test.json:17-40)
+    (None, 30000, 40, 1024, 100, "f16"),             # clip-RN50 dimension
 ])
 def test_16bit_modes_match_oracle_on_same_quantised_inputs(variant, N, nq, d, k, dtype):
     X, Q = make(N, nq, d, dtype)

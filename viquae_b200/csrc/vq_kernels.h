@@ -23,6 +23,7 @@ struct TcPlan {
     int n_chunks;         // residue classes G of corpus tiles; work item = (m_tile, g), tiles g, g+G, ...
     int tiles_per_chunk;
     int list_sets;        // candidate-list sets written: n_chunks * column halves
+    int classes_per_slab; // classes that share one contiguous slab of tiles (== n_chunks when there is one round)
     int nq_pad;           // m_tiles * 128 * cg
     int n_clusters;       // persistent clusters launched
 };
@@ -32,6 +33,7 @@ struct TcParams {
     long long n_rows;
     int nq, nq_pad, k, num_kb, m_tiles, n_tiles, n_chunks, tiles_per_chunk;
     int tile_begin;       // first corpus tile of this pass (n_tiles is the absolute end)
+    int classes_per_slab;
     int list_set_base;    // first candidate-list set this pass writes
     const float* init_thr;  // optional primed per-query thresholds: init_thr[q * init_thr_stride]
     int init_thr_stride;

@@ -202,6 +202,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
+// Corpus tiles of residue class `g` in this pass.  The G classes are grouped into slabs of `cps` consecutive
+// classes; slab s owns a contiguous range of tiles (proportional to its number of classes) and its classes
+// interleave inside it.  With one round of work items cps == G (all clusters sweep the whole pass together);
+// with several rounds each round sweeps its own slab, so every corpus byte is pulled from HBM once.
+struct TileRange { int first, end, stride; };
+__device__ __forceinline__ TileRange class_tiles(const TcParams& p, int g) {
+    const int s = g / p.classes_per_slab;
+    const int c0 = s * p.classes_per_slab;
+    const int c1 = min(p.n_chunks, c0 + p.classes_per_slab);
+    const long long span = (long long)(p.n_tiles - p.tile_begin);
+    TileRange r;
+    r.stride = c1 - c0;
+    r.first = p.tile_begin + (int)(span * c0 / p.n_chunks) + (g - c0);
+    r.end = p.tile_begin + (int)(span * c1 / p.n_chunks);
+    return r;
+}
+
 // ----------------------------------------------------------------------------- the kernel
 template <int CG>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -258,7 +275,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int m_tile = item % p.m_tiles, chunk = item / p.m_tiles;
                 const int q_row0 = (m_tile * CG + (int)rank) * BLOCK_Q;
-                for (int t = p.tile_begin + chunk; t < p.n_tiles; t += p.n_chunks) {
+                const TileRange tr = class_tiles(p, chunk);
+                for (int t = tr.first; t < tr.end; t += tr.stride) {
                     const int x_row0 = t * BLOCK_N + (int)rank * C::LOAD_N;
                     for (int kb = 0; kb < num_kb; kb++) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -281,7 +299,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             uint32_t stage = 0, phase = 0, iter = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int chunk = item / p.m_tiles;
-                for (int t = p.tile_begin + chunk; t < p.n_tiles; t += p.n_chunks, iter++) {
+                const TileRange tr = class_tiles(p, chunk);
+                for (int t = tr.first; t < tr.end; t += tr.stride, iter++) {
                     const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                     mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
                     tc_fence_after();
@@ -323,7 +342,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             // primed threshold: the k-th best score of an already-searched sample of the corpus (rows below
             // tile_begin * 256), a valid lower bound of the final k-th score; ties lose (higher row id)
             float thr = active ? (p.init_thr ? p.init_thr[(size_t)q * p.init_thr_stride] : -FLT_MAX) : INFINITY;
-            for (int t = p.tile_begin + chunk; t < p.n_tiles; t += p.n_chunks, iter++) {
+            const TileRange tr = class_tiles(p, chunk);
+            for (int t = tr.first; t < tr.end; t += tr.stride, iter++) {
                 const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                 mbar_wait(&tmem_full_bar[as], aphase);
                 tc_fence_after();
@@ -468,6 +488,12 @@ void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan) {
     plan->n_tiles = n_tiles;
     plan->n_chunks = best_c;
     plan->tiles_per_chunk = n_tiles > 0 ? (n_tiles + best_c - 1) / best_c : 1;
+    {   // classes per slab: one round -> a single slab; several rounds -> the classes a round can hold
+        const long long items_all = (long long)m_tiles * best_c;
+        plan->classes_per_slab = items_all <= n_clusters_max ? best_c : (n_clusters_max + m_tiles - 1) / m_tiles;
+        if (plan->classes_per_slab < 1) plan->classes_per_slab = 1;
+        if (plan->classes_per_slab > best_c) plan->classes_per_slab = best_c;
+    }
     plan->list_sets = best_c * tc::EPI_HALVES;
     plan->nq_pad = m_tiles * tc::BLOCK_Q * cg;
     const long long items = (long long)plan->m_tiles * plan->n_chunks;
@@ -501,6 +527,7 @@ int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long
     p.init_thr_stride = pass.init_thr_stride;
     p.n_chunks = plan.n_chunks;
     p.tiles_per_chunk = plan.tiles_per_chunk;
+    p.classes_per_slab = plan.classes_per_slab;
     // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format bf16 = 1 / f16 = 0 (bits 7-9, 10-12), both K-major
     const uint32_t fmt = (dtype == VQ_DTYPE_BF16) ? 1u : 0u;
     p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10);
