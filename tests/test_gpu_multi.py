@@ -26,6 +26,11 @@ if rank == 0:
     full = B200FlatIndex(d=256, dtype="bf16", device=0); full.add(X)
     s0, i0 = full.search_tensors(torch.from_numpy(Q).cuda(), 100)
     assert torch.equal(i, i0) and torch.allclose(s, s0, rtol=1e-5), "sharded != single"
+sh = ShardedFlatIndex(local)
+sh.SLICE_EXCHANGE_MIN_QUERIES = 16          # force the all-to-all-by-query-slice exchange (64k-batch path)
+s2, i2 = sh.search_tensors(torch.from_numpy(Q).cuda(), 100)
+assert torch.equal(i2, i) and torch.equal(s2, s), "slice exchange != all-gather exchange"
+if rank == 0:
     print("MULTI_OK")
 dist.barrier(); dist.destroy_process_group()
 '''
