@@ -277,12 +277,14 @@ struct SearchPlan {
     vq::StreamPlan st;
     int pass_sets;  // largest number of candidate-list sets any pass writes (set 0 is the running merge)
     int nq_pad;
-    size_t off_q, off_lists, off_counts, off_thr, total;
+    size_t off_q, off_lists, off_counts, off_thr, off_prog, total;
+    int max_items;
 };
 
 static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     const long long n = (long long)idx->ntotal;
     sp->n_passes = 1;
+    sp->max_items = 0;
     if (idx->dtype == VQ_F32) {
         sp->kind = 0;
         // same threshold-priming schedule as the tensor-core path (see below), in tiles of 128 rows
@@ -342,6 +344,7 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
             for (int p = 0; p < np; p++) {
                 vq::tc_plan(nq, (long long)(sp->tile_b[p + 1] - sp->tile_b[p]) * 256, idx->n_sms, cg, &sp->tc[p]);
                 if (sp->tc[p].list_sets > sp->pass_sets) sp->pass_sets = sp->tc[p].list_sets;
+                if (sp->tc[p].m_tiles * sp->tc[p].n_chunks > sp->max_items) sp->max_items = sp->tc[p].m_tiles * sp->tc[p].n_chunks;
             }
             sp->nq_pad = sp->tc[0].nq_pad;
         }
@@ -355,6 +358,8 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     off += align256((size_t)(1 + sp->pass_sets) * sp->nq_pad * sizeof(int));
     sp->off_thr = off;
     off += align256((size_t)sp->nq_pad * sizeof(float));
+    sp->off_prog = off;
+    off += align256((size_t)sp->max_items * sizeof(int));
     sp->total = off;
 }
 
@@ -382,6 +387,7 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     uint64_t* lists = (uint64_t*)(ws + sp.off_lists);
     int* counts = (int*)(ws + sp.off_counts);
     float* thr = (float*)(ws + sp.off_thr);
+    int* progress = sp.max_items ? (int*)(ws + sp.off_prog) : nullptr;
     int rc = vq::prep_rows_launch(q, q_dtype, idx->d, qprep, idx->dtype, idx->ld, nq, idx->d, l2norm_q, s);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
     idx->launches += 1;
@@ -402,7 +408,7 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
             const bool last = p == sp.n_passes - 1;
             vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, p ? thr : nullptr, 1};
             const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 256;
-            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, rows_end, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, s);
+            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, rows_end, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, progress, s);
             // first pass: every list holds at most min(CAP, its rows); primed passes add ~16k candidates per query
             const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : 4096;
             if (!rc)

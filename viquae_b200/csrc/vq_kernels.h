@@ -34,6 +34,7 @@ struct TcParams {
     int nq, nq_pad, k, num_kb, m_tiles, n_tiles, n_chunks, tiles_per_chunk;
     int tile_begin;       // first corpus tile of this pass (n_tiles is the absolute end)
     int classes_per_slab;
+    int* progress;        // [m_tiles * n_chunks] tile counters of the L2 sharing window (may be null)
     int list_set_base;    // first candidate-list set this pass writes
     const float* init_thr;  // optional primed per-query thresholds: init_thr[q * init_thr_stride]
     int init_thr_stride;
@@ -47,7 +48,7 @@ struct TcPass {
 };
 void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan);
 int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
-                   const TcPlan& plan, const TcPass& pass, uint64_t* lists, int* counts, cudaStream_t stream);
+                   const TcPlan& plan, const TcPass& pass, uint64_t* lists, int* counts, int* progress, cudaStream_t stream);
 
 // ---- K1: fp32 exact SIMT contraction + fused top-k (vq_fp32.cu)
 struct F32Plan {
