@@ -326,7 +326,8 @@ def run_ours(args):
                 roof["traffic_source"] = tr[key]["source"]
         except Exception:
             pass
-        roof["kernel"] = {"f32": "f32_topk_kernel"}.get(args.dtype, "stream_topk_kernel" if (args.variant == "stream" or (args.variant in (None, "auto") and args.nq <= 32)) else "tc_topk_kernel")
+        roof["kernel"] = {"f32": "f32_topk_kernel"}.get(args.dtype, "stream_topk_kernel" if (args.variant == "stream" and args.nq <= 32) else "tc_topk_kernel")
+        roof["timed_region"] = "all contraction passes of a step (threshold-priming passes + main pass) and their merge kernels; excludes only the query cast"
         roof["kernel_ms"] = kern_ms
         roof["kernel_launches_timed"] = nl.value
         roof["algorithmic"] = {"flops_per_launch": flops, "bytes_per_launch": bytes_}

@@ -35,6 +35,7 @@ struct TcParams {
     int tile_begin;       // first corpus tile of this pass (n_tiles is the absolute end)
     int classes_per_slab;
     int* progress;        // [m_tiles * n_chunks] tile counters of the L2 sharing window (may be null)
+    int sync_every, sync_window;
     int list_set_base;    // first candidate-list set this pass writes
     const float* init_thr;  // optional primed per-query thresholds: init_thr[q * init_thr_stride]
     int init_thr_stride;

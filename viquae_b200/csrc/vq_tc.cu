@@ -26,6 +26,7 @@
 #include "vq_kernels.h"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace vq {
 namespace tc {
@@ -276,7 +277,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // CTA's producer warp therefore publishes its tile counter every SYNC_EVERY tiles and does not run more
         // than SYNC_WINDOW tiles ahead of the slowest member of its group.  The slowest member never waits, so the
         // protocol cannot deadlock; a bounded spin makes a lost update harmless (it only costs locality).
-        constexpr int SYNC_EVERY = 4, SYNC_WINDOW = 8, SYNC_MAX_SPINS = 50000;
+        constexpr int SYNC_MAX_SPINS = 50000;
+        const int SYNC_EVERY = p.sync_every, SYNC_WINDOW = p.sync_window;
         uint32_t stage = 0, phase = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
             const int m_tile = item % p.m_tiles, chunk = item / p.m_tiles;
@@ -567,6 +569,19 @@ int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long
     p.tiles_per_chunk = plan.tiles_per_chunk;
     p.classes_per_slab = plan.classes_per_slab;
     p.progress = progress;
+    {   // window of the L2 sharing protocol (tiles); tunable for experiments through the environment
+        static int every = 0, window = 0;
+        if (!every) {
+            const char* e = getenv("VQ_SYNC_EVERY");
+            const char* w = getenv("VQ_SYNC_WINDOW");
+            every = e ? atoi(e) : 4;
+            window = w ? atoi(w) : 8;
+            if (every < 1) every = 1;
+            if (window < 1) window = 1;
+        }
+        p.sync_every = every;
+        p.sync_window = window;
+    }
     // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format bf16 = 1 / f16 = 0 (bits 7-9, 10-12), both K-major
     const uint32_t fmt = (dtype == VQ_DTYPE_BF16) ? 1u : 0u;
     p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10);
