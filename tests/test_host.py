@@ -133,3 +133,19 @@ def test_reference_experiment_configs_parse():
                 assert name in kb.indexes
                 n_dense += 1
     assert n_dense >= 5
+
+
+def test_arrow_column_blocks_zero_copy_and_fallback():
+    datasets = pytest.importorskip("datasets")
+    from viquae_b200.ingest import arrow_column_blocks
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1000, 24)).astype(np.float32)
+    ds = datasets.Dataset.from_dict({"emb": x.tolist(), "other": list(range(1000))})
+    ds = ds.cast_column("emb", datasets.Sequence(datasets.Value("float32")))
+    got = np.concatenate(list(arrow_column_blocks(ds, "emb", max_rows=300)))
+    assert got.dtype == np.float32 and np.array_equal(got, x)
+    # a selection (indices mapping) and ragged rows go through the formatted fallback
+    sub = ds.select([5, 3, 900])
+    assert np.array_equal(np.concatenate(list(arrow_column_blocks(sub, "emb"))), x[[5, 3, 900]])
+    ds64 = datasets.Dataset.from_dict({"emb": x.astype(np.float64).tolist()})
+    assert np.allclose(np.concatenate(list(arrow_column_blocks(ds64, "emb"))), x)

@@ -209,6 +209,11 @@ class B200FlatIndex(BaseIndex):
         whose ``column`` holds the embeddings.  Rows go to the device in ``batch_size`` slices
         (the reference uses 1000-row numpy batches; the slice size only affects host staging)."""
         if column is not None and not isinstance(vectors, np.ndarray):
+            if hasattr(vectors, "with_format"):  # HF Dataset: zero-copy Arrow chunks where possible
+                from .ingest import arrow_column_blocks
+                for block in arrow_column_blocks(vectors, column, max_rows=batch_size):
+                    self.add(block)
+                return
             n = len(vectors)
             for i in range(0, n, batch_size):
                 batch = vectors[i:i + batch_size][column]

@@ -151,8 +151,15 @@ class KnowledgeBase:
         else:
             n = len(self.dataset)
             engine = B200FlatIndex(dtype=dtype, device=dev, string_factory=string_factory or "Flat", capacity=n, variant=variant)
-            for i in range(0, n, batch_size):
-                engine.add(self._column_rows(column, i, min(n, i + batch_size)))
+            if hasattr(self.dataset, "with_format"):  # HF Dataset: zero-copy Arrow chunks where possible
+                from .ingest import arrow_column_blocks
+                for block in arrow_column_blocks(self.dataset, column, max_rows=batch_size):
+                    engine.add(block)
+            else:
+                for i in range(0, n, batch_size):
+                    engine.add(self._column_rows(column, i, min(n, i + batch_size)))
+            if len(engine) != n:
+                raise RuntimeError(f"ingested {len(engine)} rows of column '{column}' but the dataset has {n}")
             if save_path is not None:
                 engine.save(save_path)
         self._engines[index_name] = engine
