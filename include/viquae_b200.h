@@ -56,7 +56,8 @@ void vq_index_destroy(vq_index* idx);
 /* faiss Index::add(n, x)                                    [datasets/search.py:311-313]
  * x: [n, d] row-major, host or device pointer, element type src_dtype.  The engine copies, converts
  * to the storage dtype and (l2norm != 0) L2-normalises rows on ingest, which is what the
- * "L2norm,Flat" factory string does on add (meerqat/ir/search.py:230-245). */
+ * "L2norm,Flat" factory string does on add (meerqat/ir/search.py:230-245).  At most 2^31-256 rows per index
+ * (shard): rows travel as uint32 in the candidate keys and as int32 TMA coordinates. */
 int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2norm, void* stream);
 
 /* faiss Index::ntotal / Index::d */

@@ -196,7 +196,8 @@ static int grow(vq_index* idx, uint64_t need, cudaStream_t s) {
 int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2norm, void* stream) {
     if (!idx || (!x && n) || !dtype_ok(src_dtype)) return fail(VQ_ERR_INVALID, "vq_index_add: bad arguments");
     if (n == 0) return VQ_OK;
-    if (idx->ntotal + n > 0xFFFFFFFEull) return fail(VQ_ERR_UNSUPPORTED, "vq_index_add: more than 2^32-2 rows per shard");
+    // rows are uint32 in the candidate keys and int32 TMA coordinates in the tensor-core kernel
+    if (idx->ntotal + n > 0x7FFFFF00ull) return fail(VQ_ERR_UNSUPPORTED, "vq_index_add: more than 2^31-256 rows per shard");
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(idx->device));
     int rc = grow(idx, idx->ntotal + n, s);

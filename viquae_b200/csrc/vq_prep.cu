@@ -3,7 +3,8 @@
 // Replaces the reference's numpy L2norm (meerqat/ir/search.py:43-46: q / ||q||_2, no epsilon, so a
 // zero row becomes NaN exactly like the reference) and FAISS's NormalizationTransform for
 // "L2norm,Flat" (search.py:230-245), fused with the fp32 -> bf16/fp16 cast of the storage dtype.
-// One warp per row, 128-bit loads where the row stride allows it; HBM-bound.
+// One warp per row, lane-strided (fully coalesced) element loads/stores; HBM-bound and off the search path's
+// critical section (runs once per ingest batch and once per query batch).
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
