@@ -107,6 +107,10 @@ int vq_prep_rows(const void* src, int src_dtype, void* dst, int dst_dtype, uint6
  * scores float32 / ids int64 [n_lists, nq, k_in] (id < 0 = padding) -> [nq, k_out]. */
 int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out, float* out_scores,
                   int64_t* out_ids, void* stream);
+/* Same merge when every rank's (scores, ids) travel in ONE packed all-gather buffer: list c starts
+ * list_stride_scores floats / list_stride_ids int64s after list c-1. */
+int vq_merge_topk_strided(const float* scores, const int64_t* ids, int64_t list_stride_scores, int64_t list_stride_ids, int n_lists,
+                          int nq, int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream);
 
 /* Searcher.__call__'s per-hit post-processing (meerqat/ir/search.py:413-440) for one index and one query
  * batch: article -> passage expansion through a CSR mapping (map_offsets int64 [n_rows+1], map_targets int64

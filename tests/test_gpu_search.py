@@ -346,3 +346,21 @@ def test_full_size_corpus_properties():
     s1, i1 = idx.search_tensors(Q[:1], k)
     cmp = flat_ip.compare_results(s[:1].cpu().numpy(), i[:1].cpu().numpy(), s1.cpu().numpy(), i1.cpu().numpy(), rel_tol=1e-4)
     assert cmp["real_mismatches"] == 0, cmp
+
+
+def test_packed_merge_equals_plain_merge():
+    from viquae_b200.index import merge_topk, merge_topk_packed, packed_result_buffer
+    rng = np.random.default_rng(4)
+    G, nq, k = 3, 37, 100
+    s = np.sort(rng.standard_normal((G, nq, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    i = np.stack([rng.permutation(100000)[:nq * k].reshape(nq, k) + g * 100000 for g in range(G)]).astype(np.int64)
+    i[1, 5, 60:] = -1
+    buf, s_v, i_v = packed_result_buffer(nq, k, "cuda:0", n_lists=G)
+    for g in range(G):
+        s_v[g].copy_(torch.from_numpy(s[g]))
+        i_v[g].copy_(torch.from_numpy(i[g]))
+    a = merge_topk_packed(buf, nq, k)
+    b = merge_topk(torch.from_numpy(s).cuda(), torch.from_numpy(i).cuda())
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    Dm, Im = flat_ip.merge_topk(list(s), list(i), k)
+    assert np.array_equal(Im, a[1].cpu().numpy()) and np.array_equal(Dm, a[0].cpu().numpy())

@@ -37,6 +37,7 @@ SIGNATURES = {
     "vq_index_search_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vq_prep_rows": (c_int, [c_void_p, c_int, c_void_p, c_int, c_uint64, c_int, c_int, c_void_p]),
     "vq_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vq_merge_topk_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vq_expand_hits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                        c_void_p, c_void_p]),
     "vq_fuse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

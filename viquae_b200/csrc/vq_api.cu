@@ -492,9 +492,20 @@ int vq_prep_rows(const void* src, int src_dtype, void* dst, int dst_dtype, uint6
 int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, int k_in, int k_out, float* out_scores,
                   int64_t* out_ids, void* stream) {
     if (!scores || !ids || !out_scores || !out_ids || n_lists < 1 || nq < 0) return fail(VQ_ERR_INVALID, "vq_merge_topk: bad arguments");
-    int rc = vq::merge_topk_launch(scores, (const long long*)ids, n_lists, nq, k_in, k_out, out_scores, (long long*)out_ids, (cudaStream_t)stream);
+    int rc = vq::merge_topk_launch(scores, (const long long*)ids, (long long)nq * k_in, (long long)nq * k_in, n_lists, nq, k_in, k_out, out_scores,
+                                   (long long*)out_ids, (cudaStream_t)stream);
     if (rc == -2) return fail(VQ_ERR_UNSUPPORTED, "vq_merge_topk: k_in=%d k_out=%d not supported", k_in, k_out);
     if (rc) return fail(VQ_ERR_CUDA, "vq_merge_topk: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+int vq_merge_topk_strided(const float* scores, const int64_t* ids, int64_t list_stride_scores, int64_t list_stride_ids, int n_lists, int nq,
+                          int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream) {
+    if (!scores || !ids || !out_scores || !out_ids || n_lists < 1 || nq < 0) return fail(VQ_ERR_INVALID, "vq_merge_topk_strided: bad arguments");
+    int rc = vq::merge_topk_launch(scores, (const long long*)ids, list_stride_scores, list_stride_ids, n_lists, nq, k_in, k_out, out_scores,
+                                   (long long*)out_ids, (cudaStream_t)stream);
+    if (rc == -2) return fail(VQ_ERR_UNSUPPORTED, "vq_merge_topk_strided: k_in=%d k_out=%d not supported", k_in, k_out);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_merge_topk_strided: launch failed (%d)", rc);
     return VQ_OK;
 }
 

@@ -78,8 +78,9 @@ int stream_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long 
 int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
                        float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream);
 // per-shard results [n_lists][nq][k_in] (scores f32, ids i64; id < 0 = padding) -> [nq][k_out]
-int merge_topk_launch(const float* scores, const long long* ids, int n_lists, int nq, int k_in, int k_out,
-                      float* out_scores, long long* out_ids, cudaStream_t stream);
+// list c starts at scores + c * stride_s and ids + c * stride_i (elements)
+int merge_topk_launch(const float* scores, const long long* ids, long long stride_s, long long stride_i, int n_lists, int nq, int k_in,
+                      int k_out, float* out_scores, long long* out_ids, cudaStream_t stream);
 
 // ---- K6: run post-processing (vq_post.cu)
 int expand_hits_launch(const float* scores, const long long* ids, int nq, int k_in, const long long* map_offsets,

@@ -147,8 +147,8 @@ merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int u
 
 // Cross-GPU merge: per query, the G per-shard top-k lists [n_lists][nq][k_in] -> global top-k_out.
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, int n_lists, int nq, int k_in, int k_out,
-                  float* __restrict__ out_scores, long long* __restrict__ out_ids, int cap) {
+merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long stride_s, long long stride_i, int n_lists,
+                  int nq, int k_in, int k_out, float* __restrict__ out_scores, long long* __restrict__ out_ids, int cap) {
     extern __shared__ uint64_t keys[];
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,9 +159,9 @@ merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict_
         const int n = (c1 - c0) * k_in;
         for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
             const int c = c0 + i / k_in, j = i - (i / k_in) * k_in;
-            const size_t at = ((size_t)c * nq + q) * k_in + j;
-            const long long id = ids[at];
-            keys[i] = id >= 0 ? make_key(scores[at], (uint32_t)id) : 0ull;  // padding sorts last
+            const size_t at = (size_t)q * k_in + j;  // list c starts stride_s / stride_i elements after list c-1
+            const long long id = ids[(size_t)c * stride_i + at];
+            keys[i] = id >= 0 ? make_key(scores[(size_t)c * stride_s + at], (uint32_t)id) : 0ull;  // padding sorts last
         }
         __syncthreads();
         fold_chunks(keys, n, run, warp, lane);
@@ -210,8 +210,8 @@ int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin
     return e == cudaSuccess ? 0 : -(int)e;
 }
 
-int merge_topk_launch(const float* scores, const long long* ids, int n_lists, int nq, int k_in, int k_out,
-                      float* out_scores, long long* out_ids, cudaStream_t stream) {
+int merge_topk_launch(const float* scores, const long long* ids, long long stride_s, long long stride_i, int n_lists, int nq, int k_in,
+                      int k_out, float* out_scores, long long* out_ids, cudaStream_t stream) {
     if (nq <= 0) return 0;
     if (k_in < 1 || k_out < 1 || k_out > VQ_KMAX || k_in > MERGE_CAP_MAX) return -2;
     const int cap = pick_cap((long long)n_lists * k_in, k_in > k_out ? k_in : k_out);
@@ -225,7 +225,7 @@ int merge_topk_launch(const float* scores, const long long* ids, int n_lists, in
         if (e != cudaSuccess) return -(int)e;
         attr_set = true;
     }
-    merge_topk_kernel<<<nq, MERGE_THREADS, smem, stream>>>(scores, ids, n_lists, nq, k_in, k_out, out_scores, out_ids, cap);
+    merge_topk_kernel<<<nq, MERGE_THREADS, smem, stream>>>(scores, ids, stride_s, stride_i, n_lists, nq, k_in, k_out, out_scores, out_ids, cap);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
 }

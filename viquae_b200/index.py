@@ -231,9 +231,10 @@ class B200FlatIndex(BaseIndex):
             self._ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=f"cuda:{self.device}")
         return self._ws
 
-    def search_tensors(self, queries, k: int = 100, l2norm: Optional[bool] = None):
+    def search_tensors(self, queries, k: int = 100, l2norm: Optional[bool] = None, out=None):
         """Device-resident search: ``queries`` a cuda tensor [nq, d] (f32/bf16/f16) -> (scores f32 [nq, k],
-        ids int64 [nq, k]) cuda tensors.  Asynchronous on the current stream."""
+        ids int64 [nq, k]) cuda tensors (written into ``out=(scores, ids)`` when given).  Asynchronous on the
+        current stream."""
         torch = _torch()
         if self._h is None:
             raise RuntimeError("empty index: add vectors first")
@@ -244,8 +245,12 @@ class B200FlatIndex(BaseIndex):
         q = queries.contiguous()
         nq = q.shape[0]
         dev = f"cuda:{self.device}"
-        scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if out is not None:
+            scores, ids = out
+            assert scores.shape == (nq, k) and ids.shape == (nq, k) and scores.is_contiguous() and ids.is_contiguous()
+        else:
+            scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         if nq == 0:
             return scores, ids
         lib = _lib.load()
@@ -338,7 +343,36 @@ def merge_topk(scores, ids, k_out: Optional[int] = None):
     out_s = torch.empty((nq, k_out), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((nq, k_out), dtype=torch.int64, device=scores.device)
     if nq:
-        stream = torch.cuda.current_stream(scores.device).cuda_stream
-        _lib.check(_lib.load().vq_merge_topk(scores.data_ptr(), ids.data_ptr(), n_lists, nq, k_in, k_out, out_s.data_ptr(),
-                                             out_i.data_ptr(), stream))
+        with torch.cuda.device(scores.device):
+            stream = torch.cuda.current_stream(scores.device).cuda_stream
+            _lib.check(_lib.load().vq_merge_topk(scores.data_ptr(), ids.data_ptr(), n_lists, nq, k_in, k_out, out_s.data_ptr(),
+                                                 out_i.data_ptr(), stream))
+    return out_s, out_i
+
+
+def packed_result_buffer(nq: int, k: int, device, n_lists: int = 1):
+    """One byte buffer per list holding scores (f32 [nq, k]) then ids (i64 [nq, k]), so that the candidates of a
+    rank travel in ONE all-gather.  Returns (buffer uint8 [n_lists, nbytes], scores views, ids views)."""
+    torch = _torch()
+    s_bytes = (nq * k * 4 + 7) // 8 * 8
+    nbytes = s_bytes + nq * k * 8
+    buf = torch.empty((n_lists, nbytes), dtype=torch.uint8, device=device)
+    scores = [buf[c, :nq * k * 4].view(torch.float32).view(nq, k) for c in range(n_lists)]
+    ids = [buf[c, s_bytes:].view(torch.int64).view(nq, k) for c in range(n_lists)]
+    return buf, scores, ids
+
+
+def merge_topk_packed(buf, nq: int, k_in: int, k_out: Optional[int] = None):
+    """K4 over a gathered packed buffer [n_lists, nbytes] (see ``packed_result_buffer``)."""
+    torch = _torch()
+    n_lists, nbytes = buf.shape
+    k_out = k_in if k_out is None else k_out
+    s_bytes = (nq * k_in * 4 + 7) // 8 * 8
+    out_s = torch.empty((nq, k_out), dtype=torch.float32, device=buf.device)
+    out_i = torch.empty((nq, k_out), dtype=torch.int64, device=buf.device)
+    if nq:
+        with torch.cuda.device(buf.device):
+            stream = torch.cuda.current_stream(buf.device).cuda_stream
+            _lib.check(_lib.load().vq_merge_topk_strided(buf.data_ptr(), buf.data_ptr() + s_bytes, nbytes // 4, nbytes // 8, n_lists, nq, k_in,
+                                                         k_out, out_s.data_ptr(), out_i.data_ptr(), stream))
     return out_s, out_i

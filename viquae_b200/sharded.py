@@ -35,6 +35,7 @@ class ShardedFlatIndex:
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.local_index = local_index
+        self._packed_ok = local_search is None and merge is None and local_index is not None
         if local_search is None:
             if local_index is None:
                 raise ValueError("need a local index")
@@ -75,6 +76,16 @@ class ShardedFlatIndex:
         Returns the global (scores [nq, k], ids [nq, k]) on every rank."""
         import torch
 
+        if (self.world_size > 1 and self._packed_ok and queries.shape[0] < self.SLICE_EXCHANGE_MIN_QUERIES
+                and self.dist.get_backend(self.group) == "nccl"):
+            # scores + ids of this rank in one buffer -> ONE all-gather -> strided K4 merge
+            from .index import merge_topk_packed, packed_result_buffer
+            nq = queries.shape[0]
+            mine, s_v, i_v = packed_result_buffer(nq, k, queries.device)
+            self.local_index.search_tensors(queries, k, out=(s_v[0], i_v[0]))
+            gathered = torch.empty((self.world_size, mine.shape[1]), dtype=torch.uint8, device=queries.device)
+            self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            return merge_topk_packed(gathered, nq, k)
         s_loc, i_loc = self._local_search(queries, k)
         if self.world_size == 1:
             return s_loc, i_loc
