@@ -364,3 +364,28 @@ def test_packed_merge_equals_plain_merge():
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     Dm, Im = flat_ip.merge_topk(list(s), list(i), k)
     assert np.array_equal(Im, a[1].cpu().numpy()) and np.array_equal(Dm, a[0].cpu().numpy())
+
+
+def test_randomized_small_shapes_all_paths():
+    """Seeded fuzz over awkward shapes (d = 1.., N = 1.., k = 1..128, nq = 1..300) on every kernel family."""
+    rng = np.random.default_rng(2024)
+    for trial in range(36):
+        d = int(rng.choice([1, 2, 3, 7, 8, 9, 31, 63, 64, 65, 100, 129, 200, 384]))
+        N = int(rng.choice([1, 2, 5, 100, 255, 256, 257, 511, 1000, 4097]))
+        nq = int(rng.choice([1, 2, 31, 33, 127, 128, 129, 257, 300]))
+        k = int(rng.choice([1, 2, 5, 64, 100, 127, 128]))
+        dtype, variant = [("bf16", None), ("bf16", "tc_cg1"), ("bf16", "tc_cg2"), ("f16", None), ("f32", None), ("bf16", "stream")][trial % 6]
+        if variant == "stream":
+            nq = min(nq, 32)
+        X, Q = make(N, nq, d, dtype, seed=100 + trial)
+        idx = engine(X, dtype, variant)
+        res = idx.search_batch(Q, k)
+        D, I = np.asarray(res.total_scores), np.asarray(res.total_indices)
+        if dtype == "f32":
+            Dr, Ir = c_oracle.flat_ip(Q, X, k)
+            assert np.array_equal(I, Ir) and np.array_equal(D.view(np.uint32), Dr.view(np.uint32)), (trial, d, N, nq, k)
+        else:
+            Dr, Ir = flat_ip.flat_ip_search(Q, X, k)
+            cmp = flat_ip.compare_results(Dr, Ir, D, I, rel_tol=REL_TOL_16, abs_tol=1e-4)
+            assert cmp["real_mismatches"] == 0 and (I >= 0).sum() == (Ir >= 0).sum(), (trial, d, N, nq, k, dtype, variant, cmp)
+        idx.close()
