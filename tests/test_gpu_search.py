@@ -389,3 +389,27 @@ def test_randomized_small_shapes_all_paths():
             cmp = flat_ip.compare_results(Dr, Ir, D, I, rel_tol=REL_TOL_16, abs_tol=1e-4)
             assert cmp["real_mismatches"] == 0 and (I >= 0).sum() == (Ir >= 0).sum(), (trial, d, N, nq, k, dtype, variant, cmp)
         idx.close()
+
+
+def test_knowledgebase_save_path_then_load(tmp_path):
+    """`save_path` / `load` of the index config (meerqat/ir/search.py:234-248), through KnowledgeBase."""
+    from viquae_b200.search import KnowledgeBase
+    rng = np.random.default_rng(12)
+    emb = rng.standard_normal((800, 40)).astype(np.float32)
+    q = rng.standard_normal((9, 40)).astype(np.float32)
+
+    class DictDS(dict):
+        def __len__(self):
+            return len(next(iter(self.values())))
+    path = str(tmp_path / "clip.index")
+    kb1 = KnowledgeBase(dataset=DictDS({"e": emb}), index_kwargs={"clip": {"column": "e", "key": "q", "string_factory": "L2norm,Flat",
+                                                                            "metric_type": 0, "save_path": path}})
+    kb2 = KnowledgeBase(dataset=DictDS({"e": emb}), index_kwargs={"clip": {"column": "e", "key": "q", "string_factory": "L2norm,Flat",
+                                                                            "metric_type": 0, "load": True, "file": path}})
+    assert kb2.indexes["clip"].do_L2norm is True
+    s1, i1 = kb1.search_batch("clip", q, k=10)
+    s2, i2 = kb2.search_batch("clip", q, k=10)
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+    with pytest.raises(ValueError, match="Index size should match"):
+        KnowledgeBase(dataset=DictDS({"e": emb[:10]}), index_kwargs={"clip": {"column": "e", "key": "q", "string_factory": "L2norm,Flat",
+                                                                              "metric_type": 0, "load": True, "file": path}})
