@@ -31,7 +31,7 @@ extern "C" {
 #define VQ_OK 0
 #define VQ_ERR_CUDA (-1)        /* a CUDA runtime/driver call failed (see vq_last_error) */
 #define VQ_ERR_INVALID (-2)     /* bad argument (shape, dtype, k, null pointer) */
-#define VQ_ERR_UNSUPPORTED (-3) /* valid request the engine does not serve (e.g. k > 128) */
+#define VQ_ERR_UNSUPPORTED (-3) /* valid request the engine does not serve (e.g. k > 2048) */
 #define VQ_ERR_NOMEM (-4)       /* workspace too small / allocation failed */
 
 /* kernel variants (vq_index_set_variant): 0 lets the engine choose from (dtype, nq) */
@@ -88,7 +88,9 @@ size_t vq_index_workspace_bytes(const vq_index* idx, int nq, int k);
  * All pointers are DEVICE pointers.  q: [nq, d] of q_dtype; l2norm_q != 0 applies the reference's
  * L2norm(queries) (meerqat/ir/search.py:43-46,144-145).  Outputs: out_scores float32 [nq, k] sorted
  * descending, out_ids int64 [nq, k]; rows with fewer than k hits are padded with (-FLT_MAX, -1);
- * equal scores are ordered by lower id.  Asynchronous on `stream`. */
+ * equal scores are ordered by lower id.  k <= 128 is one fused search; 128 < k <= 2048 runs ceil(k/128) banded
+ * rounds (each round takes what ranks strictly after the previous round's last hit), still exact.
+ * Asynchronous on `stream`. */
 int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2norm_q, int k, float* out_scores,
                     int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -109,7 +109,7 @@ def test_edge_cases():
         idx.search_batch(np.zeros((2, 63), np.float32), 5)
     from viquae_b200._lib import EngineError
     with pytest.raises(EngineError):
-        idx.search_batch(Q, 129)                                                             # k > 128: refused, not approximated
+        idx.search_batch(Q, 2049)                                                            # k > 2048: refused, not approximated
     one = idx.search(Q[0], 7)                                                                 # FaissIndex.search: one vector
     assert len(one.scores) == 7 and np.array_equal(np.asarray(one.indices), I[0, :7])
     empty = B200FlatIndex(d=64, dtype="bf16")
@@ -413,3 +413,41 @@ def test_knowledgebase_save_path_then_load(tmp_path):
     with pytest.raises(ValueError, match="Index size should match"):
         KnowledgeBase(dataset=DictDS({"e": emb[:10]}), index_kwargs={"clip": {"column": "e", "key": "q", "string_factory": "L2norm,Flat",
                                                                               "metric_type": 0, "load": True, "file": path}})
+
+
+@pytest.mark.parametrize("dtype,N,nq,d,k", [("bf16", 30000, 140, 256, 129), ("bf16", 50000, 40, 768, 1000), ("f16", 3000, 9, 64, 300),
+                                            ("f32", 6000, 33, 96, 500), ("bf16", 700, 5, 32, 2048), ("bf16", 300000, 260, 128, 257)])
+def test_large_k_banded_rounds(dtype, N, nq, d, k):
+    """k > 128: ceil(k/128) banded rounds, each taking what ranks strictly after the previous round's last hit.
+    Exactness and tie order must be those of a single top-k (N < k pads with -1)."""
+    X, Q = make(N, nq, d, dtype, seed=5)
+    X[100:130] = X[99]            # a run of exact ties that straddles a band boundary for some queries
+    idx = engine(X, dtype)
+    res = idx.search_batch(Q, k)
+    D, I = np.asarray(res.total_scores), np.asarray(res.total_indices)
+    if dtype == "f32":
+        Dr, Ir = c_oracle.flat_ip(Q, X, k)
+        assert np.array_equal(I, Ir) and np.array_equal(D.view(np.uint32), Dr.view(np.uint32))
+    else:
+        Dr, Ir = flat_ip.flat_ip_search(Q, X, k)
+        cmp = flat_ip.compare_results(Dr, Ir, D, I, rel_tol=REL_TOL_16, abs_tol=1e-4)
+        assert cmp["real_mismatches"] == 0 and cmp["overlap"] >= MIN_OVERLAP and (I >= 0).sum() == (Ir >= 0).sum(), cmp
+    valid = I >= 0
+    assert all(len(set(row[v].tolist())) == v.sum() for row, v in zip(I, valid)), "an id was returned twice across bands"
+    assert np.all(np.diff(np.where(valid, D, -np.inf), axis=1) <= 0)
+
+
+def test_large_k_cross_shard_merge():
+    from viquae_b200.index import B200FlatIndex, merge_topk
+    X, Q = make(6000, 12, 64, "bf16", seed=8)
+    k = 400
+    full = engine(X, "bf16")
+    s_full, i_full = full.search_tensors(torch.from_numpy(Q).cuda(), k)
+    parts = []
+    for a, b in ((0, 2500), (2500, 6000)):
+        sh = B200FlatIndex(d=64, dtype="bf16", id_offset=a)
+        sh.add(X[a:b])
+        parts.append(sh.search_tensors(torch.from_numpy(Q).cuda(), k))
+    s_m, i_m = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    cmp = flat_ip.compare_results(s_full.cpu().numpy(), i_full.cpu().numpy(), s_m.cpu().numpy(), i_m.cpu().numpy(), rel_tol=1e-5)
+    assert cmp["real_mismatches"] == 0 and cmp["overlap"] == 1.0, cmp

@@ -380,31 +380,89 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     sp->total = off;
 }
 
+// extra workspace of banded searches: one round's [nq][128] results + the per-query bound
+static size_t band_bytes(int nq, int nq_pad) {
+    return align256((size_t)nq * VQ_KMAX * sizeof(float)) + align256((size_t)nq * VQ_KMAX * sizeof(long long)) +
+           align256((size_t)nq_pad * sizeof(float)) + align256((size_t)nq_pad * sizeof(uint32_t));
+}
+
 size_t vq_index_workspace_bytes(const vq_index* idx, int nq, int k) {
-    (void)k;
     if (!idx || nq <= 0) return 0;
     SearchPlan sp;
     make_plan(idx, nq, &sp);
-    return sp.total;
+    return sp.total + (k > VQ_KMAX ? band_bytes(nq, sp.nq_pad) : 0);
 }
+
+// One full search of at most VQ_KMAX results per query (all priming passes + merges).  With ub_score/ub_row set,
+// only candidates ranking strictly after that per-query bound are taken (banded rounds for k > VQ_KMAX).
+static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const void* qprep, int nq, int k, const float* ub_score,
+                        const uint32_t* ub_row, long long id_offset, float* out_scores, long long* out_ids, cudaStream_t s) {
+    uint64_t* lists = (uint64_t*)(ws + sp.off_lists);
+    int* counts = (int*)(ws + sp.off_counts);
+    float* thr = (float*)(ws + sp.off_thr);
+    int* progress = sp.max_items ? (int*)(ws + sp.off_prog) : nullptr;
+    const long long ntot = (long long)idx->ntotal;
+    int rc = 0;
+    if (ntot == 0) {
+        cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(1 + sp.pass_sets) * sp.nq_pad * sizeof(int), s);
+        if (e != cudaSuccess) return -(int)e;
+        rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, id_offset, nullptr, out_scores, out_ids, 512, s);
+        idx->launches += 1;
+    } else if (sp.kind == 1) {
+        for (int p = 0; p < sp.n_passes && !rc; p++) {
+            const bool last = p == sp.n_passes - 1;
+            vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, p ? thr : nullptr, 1, ub_score, ub_row};
+            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 256;
+            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, rows_end, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, progress, s);
+            // first pass: every row is a candidate; primed passes add ~ratio * k candidates per query
+            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : 4096;
+            if (!rc)
+                rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.tc[p].list_sets, sp.nq_pad, nq, k, id_offset, last ? nullptr : thr,
+                                            last ? out_scores : nullptr, last ? out_ids : nullptr, expected, s);
+            idx->launches += 2;
+        }
+    } else if (sp.kind == 0) {
+        for (int p = 0; p < sp.n_passes && !rc; p++) {
+            const bool last = p == sp.n_passes - 1;
+            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 128;
+            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, rows_end, idx->ld, idx->d, k, sp.f32[p],
+                                     sp.tile_b[p], sp.tile_b[p + 1], p ? thr : nullptr, ub_score, ub_row,
+                                     lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
+            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 128 + k : 4096;
+            if (!rc)
+                rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.f32[p].n_chunks, sp.nq_pad, nq, k, id_offset, last ? nullptr : thr,
+                                            last ? out_scores : nullptr, last ? out_ids : nullptr, expected, s);
+            idx->launches += 2;
+        }
+    } else {
+        if (ub_score) return -3;  // the streaming kernel has no banded mode
+        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.st,
+                                    lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
+        if (!rc)
+            rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, id_offset, nullptr, out_scores, out_ids,
+                                        sp.pass_sets * k, s);
+        idx->launches += 2;
+    }
+    return rc;
+}
+
+#define VQ_KMAX_BANDED 2048
 
 int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2norm_q, int k, float* out_scores, int64_t* out_ids,
                     void* workspace, size_t workspace_bytes, void* stream) {
     if (!idx || nq < 0 || k < 1 || !dtype_ok(q_dtype)) return fail(VQ_ERR_INVALID, "vq_index_search: bad arguments (nq=%d k=%d)", nq, k);
     if (nq == 0) return VQ_OK;
     if (!q || !out_scores || !out_ids || !workspace) return fail(VQ_ERR_INVALID, "vq_index_search: null pointer");
-    if (k > VQ_KMAX) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: k=%d > %d is not served by the fused top-k path", k, VQ_KMAX);
+    if (k > VQ_KMAX_BANDED) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: k=%d > %d is not served", k, VQ_KMAX_BANDED);
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(idx->device));
     SearchPlan sp;
     make_plan(idx, nq, &sp);
-    if (workspace_bytes < sp.total) return fail(VQ_ERR_NOMEM, "vq_index_search: workspace %zu < %zu bytes", workspace_bytes, sp.total);
+    if (k > VQ_KMAX && sp.kind == 2) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: the streaming variant serves k <= %d", VQ_KMAX);
+    const size_t need = sp.total + (k > VQ_KMAX ? band_bytes(nq, sp.nq_pad) : 0);
+    if (workspace_bytes < need) return fail(VQ_ERR_NOMEM, "vq_index_search: workspace %zu < %zu bytes", workspace_bytes, need);
     uint8_t* ws = (uint8_t*)workspace;
     void* qprep = ws + sp.off_q;
-    uint64_t* lists = (uint64_t*)(ws + sp.off_lists);
-    int* counts = (int*)(ws + sp.off_counts);
-    float* thr = (float*)(ws + sp.off_thr);
-    int* progress = sp.max_items ? (int*)(ws + sp.off_prog) : nullptr;
     int rc = vq::prep_rows_launch(q, q_dtype, idx->d, qprep, idx->dtype, idx->ld, nq, idx->d, l2norm_q, s);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
     idx->launches += 1;
@@ -415,45 +473,24 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
                                  (size_t)(sp.nq_pad - nq) * idx->ld * esize(idx->dtype), s));
     const bool timed = idx->timing && idx->n_timed < VQ_TIMING_SLOTS && idx->ntotal;
     if (timed) CUDA_TRY(cudaEventRecord(idx->ev0[idx->n_timed], s));
-    const long long ntot = (long long)idx->ntotal;
-    if (ntot == 0) {
-        CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)(1 + sp.pass_sets) * sp.nq_pad * sizeof(int), s));
-        rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, idx->id_offset, nullptr, out_scores, (long long*)out_ids, 512, s);
-        idx->launches += 1;
-    } else if (sp.kind == 1) {
-        for (int p = 0; p < sp.n_passes && !rc; p++) {
-            const bool last = p == sp.n_passes - 1;
-            vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, p ? thr : nullptr, 1};
-            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 256;
-            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, rows_end, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, progress, s);
-            // first pass: every list holds at most min(CAP, its rows); primed passes add ~16k candidates per query
-            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : 4096;
-            if (!rc)
-                rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.tc[p].list_sets, sp.nq_pad, nq, k, idx->id_offset, last ? nullptr : thr,
-                                            last ? out_scores : nullptr, last ? (long long*)out_ids : nullptr, expected, s);
-            idx->launches += 2;
-        }
-    } else if (sp.kind == 0) {
-        for (int p = 0; p < sp.n_passes && !rc; p++) {
-            const bool last = p == sp.n_passes - 1;
-            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 128;
-            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, rows_end, idx->ld, idx->d, k, sp.f32[p],
-                                     sp.tile_b[p], sp.tile_b[p + 1], p ? thr : nullptr, lists + (size_t)sp.nq_pad * VQ_CAP,
-                                     counts + sp.nq_pad, s);
-            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 128 + k : 4096;
-            if (!rc)
-                rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.f32[p].n_chunks, sp.nq_pad, nq, k, idx->id_offset, last ? nullptr : thr,
-                                            last ? out_scores : nullptr, last ? (long long*)out_ids : nullptr, expected, s);
-            idx->launches += 2;
-        }
+    if (k <= VQ_KMAX) {
+        rc = search_round(idx, sp, ws, qprep, nq, k, nullptr, nullptr, idx->id_offset, out_scores, (long long*)out_ids, s);
     } else {
-        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.st,
-                                    lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
-        if (!rc)
-            rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, idx->id_offset, nullptr, out_scores,
-                                        (long long*)out_ids, sp.pass_sets * k, s);
-        idx->launches += 2;
+        // k > 128: rounds of up to 128 results; round r takes what ranks strictly after the last entry of round r-1
+        uint8_t* band = ws + sp.total;
+        float* tmp_s = (float*)band;
+        long long* tmp_i = (long long*)(band + align256((size_t)nq * VQ_KMAX * sizeof(float)));
+        float* ub_score = (float*)((uint8_t*)tmp_i + align256((size_t)nq * VQ_KMAX * sizeof(long long)));
+        uint32_t* ub_row = (uint32_t*)((uint8_t*)ub_score + align256((size_t)sp.nq_pad * sizeof(float)));
+        for (int col0 = 0; col0 < k && !rc; col0 += VQ_KMAX) {
+            const int kr = k - col0 < VQ_KMAX ? k - col0 : VQ_KMAX;
+            rc = search_round(idx, sp, ws, qprep, nq, kr, col0 ? ub_score : nullptr, col0 ? ub_row : nullptr, 0, tmp_s, tmp_i, s);
+            if (!rc)
+                rc = vq::band_scatter_launch(tmp_s, tmp_i, nq, kr, k, col0, idx->id_offset, out_scores, (long long*)out_ids, ub_score, ub_row, s);
+            idx->launches += 1;
+        }
     }
+    if (rc == -3) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: variant does not support k > %d", VQ_KMAX);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: kernel launch failed (%d: %s)", rc, rc < 0 && rc > -1000 ? cudaGetErrorString((cudaError_t)(-rc)) : "driver");
     if (timed) {
         CUDA_TRY(cudaEventRecord(idx->ev1[idx->n_timed], s));
@@ -473,7 +510,8 @@ int vq_index_search_host(vq_index* idx, const float* q_host, int nq, int l2norm_
     const size_t q_bytes = align256((size_t)nq * idx->d * sizeof(float));
     const size_t s_bytes = align256((size_t)nq * k * sizeof(float));
     const size_t i_bytes = align256((size_t)nq * k * sizeof(int64_t));
-    const size_t need = q_bytes + s_bytes + i_bytes + sp.total;
+    const size_t ws_need = vq_index_workspace_bytes(idx, nq, k);
+    const size_t need = q_bytes + s_bytes + i_bytes + ws_need;
     if (idx->hws_bytes < need) {
         if (idx->hws) cudaFree(idx->hws);
         idx->hws = nullptr;
@@ -489,7 +527,7 @@ int vq_index_search_host(vq_index* idx, const float* q_host, int nq, int l2norm_
     void* ws = base + q_bytes + s_bytes + i_bytes;
     cudaStream_t s = 0;
     CUDA_TRY(cudaMemcpyAsync(dq, q_host, (size_t)nq * idx->d * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = vq_index_search(idx, dq, nq, VQ_F32, l2norm_q, k, ds, di, ws, sp.total, (void*)s);
+    int rc = vq_index_search(idx, dq, nq, VQ_F32, l2norm_q, k, ds, di, ws, ws_need, (void*)s);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_scores_host, ds, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_ids_host, di, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, s));

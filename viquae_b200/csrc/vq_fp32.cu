@@ -20,11 +20,14 @@ constexpr int LDS = BM + 4;  // padded row of the k-major smem tiles
 __global__ void __launch_bounds__(THREADS, 2)
 f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __restrict__ X, long long n_rows, int ld_x, int d, int k,
                 int m_tiles, int tile_begin, int n_tiles, int n_chunks, int tiles_per_chunk, int nq_pad, const float* __restrict__ init_thr,
-                uint64_t* __restrict__ lists, int* __restrict__ counts) {
+                const float* __restrict__ ub_score, const uint32_t* __restrict__ ub_row, uint64_t* __restrict__ lists,
+                int* __restrict__ counts) {
     __shared__ __align__(16) float As[2][BK][LDS];  // double-buffered k-major tiles
     __shared__ __align__(16) float Bs[2][BK][LDS];
     __shared__ float thr_s[BM];
     __shared__ int cnt_s[BM];
+    __shared__ float ubs_s[BM];      // exclusive upper bound of banded rounds (k > 128); +inf when unbanded
+    __shared__ uint32_t ubr_s[BM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // 16 x 16 threads, 8 x 8 outputs each as 2 x 2 blocks of 4 x 4: rows {4ty..4ty+3, 64+4ty..}, cols {4tx.., 64+4tx..}
@@ -44,6 +47,8 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
             cnt_s[tid] = 0;
             // primed threshold (k-th score of the rows of earlier passes, all with lower ids) or -FLT_MAX
             thr_s[tid] = (q0 + tid < nq) ? (init_thr ? init_thr[q0 + tid] : -FLT_MAX) : INFINITY;
+            ubs_s[tid] = (ub_score && q0 + tid < nq) ? ub_score[q0 + tid] : INFINITY;
+            ubr_s[tid] = (ub_row && q0 + tid < nq) ? ub_row[q0 + tid] : 0u;
         }
         __syncthreads();
         const int t0 = tile_begin + chunk * tiles_per_chunk;
@@ -125,12 +130,14 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
             for (int i = 0; i < 8; i++) {
                 const int r = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
                 const float thr = thr_s[r];
+                const float ubs = ubs_s[r];
+                const uint32_t ubr = ubr_s[r];
                 unsigned long long* list = reinterpret_cast<unsigned long long*>(item_lists + (size_t)r * VQ_CAP);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const long long xr = x0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
                     const float s = acc[i][j];
-                    if (xr < n_rows && s > thr) {
+                    if (xr < n_rows && s > thr && (s < ubs || (s == ubs && (uint32_t)xr > ubr))) {
                         const int pos = atomicAdd(&cnt_s[r], 1);
                         __stcg(list + pos, (unsigned long long)pack_raw(s, (uint32_t)xr));
                     }
@@ -189,12 +196,12 @@ void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan) {
 }
 
 int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
-                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, uint64_t* lists, int* counts,
-                    cudaStream_t stream) {
+                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, const float* ub_score,
+                    const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream) {
     if (k < 1 || k > VQ_KMAX) return -2;
     if (nq <= 0) return 0;
     f32::f32_topk_kernel<<<plan.n_ctas, f32::THREADS, 0, stream>>>(q, nq, ld_q, x, n_rows, ld_x, d, k, plan.m_tiles, tile_begin, tile_end,
-                                                                  plan.n_chunks, plan.tiles_per_chunk, plan.nq_pad, init_thr, lists, counts);
+                                                                  plan.n_chunks, plan.tiles_per_chunk, plan.nq_pad, init_thr, ub_score, ub_row, lists, counts);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -39,6 +39,10 @@ struct TcParams {
     int list_set_base;    // first candidate-list set this pass writes
     const float* init_thr;  // optional primed per-query thresholds: init_thr[q * init_thr_stride]
     int init_thr_stride;
+    // optional exclusive UPPER bound per query (banded rounds for k > 128): only candidates that rank strictly
+    // after (ub_score[q], ub_row[q]) are taken
+    const float* ub_score;
+    const uint32_t* ub_row;
     uint32_t idesc_base;
 };
 // one pass over corpus tiles [tile_begin, tile_end): plan must come from tc_plan(nq, (tile_end - tile_begin) * 256 rows)
@@ -46,6 +50,8 @@ struct TcPass {
     int tile_begin, tile_end, list_set_base;
     const float* init_thr;
     int init_thr_stride;
+    const float* ub_score;
+    const uint32_t* ub_row;
 };
 void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan);
 int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
@@ -58,8 +64,8 @@ struct F32Plan {
 void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan);
 // one pass over corpus tiles (128 rows each) [tile_begin, tile_end); plan from f32_plan(nq, (tile_end - tile_begin) * 128 rows)
 int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
-                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, uint64_t* lists, int* counts,
-                    cudaStream_t stream);
+                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, const float* ub_score,
+                    const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream);
 
 // ---- K2: small-batch HBM-streaming contraction + fused top-k (vq_stream.cu)
 struct StreamPlan {
@@ -77,6 +83,10 @@ int stream_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long 
 // given, the final [nq][k] scores (f32) / ids (i64, + id_offset).  expected_total sizes the shared-memory sort.
 int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
                        float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream);
+// banded rounds (k > 128): copies one round's [nq][kr] result into columns [col0, col0+kr) of the final [nq][k]
+// outputs (+ id_offset) and sets the next round's exclusive upper bound to the round's last entry
+int band_scatter_launch(const float* tmp_s, const long long* tmp_i, int nq, int kr, int k, int col0, long long id_offset,
+                        float* out_scores, long long* out_ids, float* ub_score, uint32_t* ub_row, cudaStream_t stream);
 // per-shard results [n_lists][nq][k_in] (scores f32, ids i64; id < 0 = padding) -> [nq][k_out]
 // list c starts at scores + c * stride_s and ids + c * stride_i (elements)
 int merge_topk_launch(const float* scores, const long long* ids, long long stride_s, long long stride_i, int n_lists, int nq, int k_in,

@@ -181,6 +181,66 @@ merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict_
     }
 }
 
+__global__ void band_scatter_kernel(const float* __restrict__ tmp_s, const long long* __restrict__ tmp_i, int nq, int kr, int k, int col0,
+                                    long long id_offset, float* __restrict__ out_scores, long long* __restrict__ out_ids,
+                                    float* __restrict__ ub_score, uint32_t* __restrict__ ub_row) {
+    const int q = blockIdx.x;
+    for (int e = threadIdx.x; e < kr; e += blockDim.x) {
+        const float s = tmp_s[(size_t)q * kr + e];
+        const long long id = tmp_i[(size_t)q * kr + e];
+        out_scores[(size_t)q * k + col0 + e] = s;
+        out_ids[(size_t)q * k + col0 + e] = id >= 0 ? id + id_offset : -1;
+        if (e == kr - 1) {
+            // next round takes what ranks strictly after this entry; a short round means the corpus is exhausted
+            ub_score[q] = id >= 0 ? s : -INFINITY;
+            ub_row[q] = id >= 0 ? (uint32_t)id : 0u;
+        }
+    }
+}
+
+int band_scatter_launch(const float* tmp_s, const long long* tmp_i, int nq, int kr, int k, int col0, long long id_offset,
+                        float* out_scores, long long* out_ids, float* ub_score, uint32_t* ub_row, cudaStream_t stream) {
+    if (nq <= 0) return 0;
+    band_scatter_kernel<<<nq, 128, 0, stream>>>(tmp_s, tmp_i, nq, kr, k, col0, id_offset, out_scores, out_ids, ub_score, ub_row);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// k_out > 128 (banded searches): gather every list of the query and sort them all in shared memory.
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_topk_big_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long stride_s, long long stride_i, int n_lists,
+                      int nq, int k_in, int k_out, float* __restrict__ out_scores, long long* __restrict__ out_ids, int S) {
+    extern __shared__ uint64_t keys[];
+    const int q = blockIdx.x;
+    const int n = n_lists * k_in;
+    for (int i = threadIdx.x; i < S; i += MERGE_THREADS) {
+        uint64_t key = 0ull;
+        if (i < n) {
+            const int c = i / k_in, j = i - c * k_in;
+            const size_t at = (size_t)q * k_in + j;
+            const long long id = ids[(size_t)c * stride_i + at];
+            if (id >= 0) key = make_key(scores[(size_t)c * stride_s + at], (uint32_t)id);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int s2 = 2; s2 <= S; s2 <<= 1)
+        for (int j = s2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (S >> 1); i += MERGE_THREADS) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                const bool desc = (lo & s2) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if (desc ? (a < b) : (a > b)) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (int e = threadIdx.x; e < k_out; e += MERGE_THREADS) {
+        const uint64_t key = e < S ? keys[e] : 0ull;
+        out_scores[(size_t)q * k_out + e] = key ? key_score(key) : -FLT_MAX;
+        out_ids[(size_t)q * k_out + e] = key ? (long long)key_row(key) : -1;
+    }
+}
+
 static int pick_cap(long long total, int k) {
     long long need = total > 2LL * k ? total : 2LL * k;
     int cap = 1024;  // also hosts the [8][128] tree buffer
@@ -213,7 +273,25 @@ int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin
 int merge_topk_launch(const float* scores, const long long* ids, long long stride_s, long long stride_i, int n_lists, int nq, int k_in,
                       int k_out, float* out_scores, long long* out_ids, cudaStream_t stream) {
     if (nq <= 0) return 0;
-    if (k_in < 1 || k_out < 1 || k_out > VQ_KMAX || k_in > MERGE_CAP_MAX) return -2;
+    if (k_in < 1 || k_out < 1 || k_in > MERGE_CAP_MAX) return -2;
+    if (k_out > VQ_KMAX) {
+        long long n = (long long)n_lists * k_in;
+        if (n > MERGE_CAP_MAX) return -2;
+        int S = 2;
+        while (S < n) S <<= 1;
+        static bool big_attr[64] = {};
+        int dev_b = 0;
+        cudaGetDevice(&dev_b);
+        if (!big_attr[dev_b & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(merge_topk_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP_MAX * 8);
+            if (e != cudaSuccess) return -(int)e;
+            big_attr[dev_b & 63] = true;
+        }
+        merge_topk_big_kernel<<<nq, MERGE_THREADS, (size_t)S * 8, stream>>>(scores, ids, stride_s, stride_i, n_lists, nq, k_in, k_out, out_scores,
+                                                                           out_ids, S);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : -(int)e;
+    }
     const int cap = pick_cap((long long)n_lists * k_in, k_in > k_out ? k_in : k_out);
     const size_t smem = (size_t)cap * sizeof(uint64_t);
     static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device

@@ -184,6 +184,40 @@ __device__ __forceinline__ void push_if_gt_imm(unsigned long long* list, uint32_
         : "l"(list), "f"(__uint_as_float(s_bits)), "f"(thr), "r"(s_bits), "r"(rbase), "n"(J)
         : "memory");
 }
+// banded variant: additionally requires (s, row) to rank strictly AFTER the bound (ubs, ubr):
+// s < ubs, or s == ubs and row > ubr
+template <int J>
+__device__ __forceinline__ void push_if_banded_imm(unsigned long long* list, uint32_t& cnt, uint32_t s_bits, float thr, uint32_t rbase,
+                                                   float ubs, uint32_t ubr) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, lt, eq, gt;\n"
+        ".reg .b64 a;\n"
+        ".reg .b32 r;\n"
+        "add.u32 r, %5, %6;\n"
+        "setp.gt.f32 p, %2, %3;\n"
+        "setp.lt.f32 lt, %2, %7;\n"
+        "setp.eq.f32 eq, %2, %7;\n"
+        "setp.gt.u32 gt, r, %8;\n"
+        "and.pred eq, eq, gt;\n"
+        "or.pred lt, lt, eq;\n"
+        "and.pred p, p, lt;\n"
+        "mad.wide.u32 a, %0, 8, %1;\n"
+        "@p st.global.cg.v2.b32 [a], {%4, r};\n"
+        "@p add.u32 %0, %0, 1;\n"
+        "}\n"
+        : "+r"(cnt)
+        : "l"(list), "f"(__uint_as_float(s_bits)), "f"(thr), "r"(s_bits), "r"(rbase), "n"(J), "f"(ubs), "r"(ubr)
+        : "memory");
+}
+template <int J0, int J1>
+__device__ __forceinline__ void push_block_banded(unsigned long long* list, uint32_t& cnt, const uint32_t (&v)[32], float thr, uint32_t rbase,
+                                                  int lim, float ubs, uint32_t ubr) {
+    if constexpr (J0 < J1) {
+        push_if_banded_imm<J0>(list, cnt, v[J0], (J0 < lim) ? thr : INFINITY, rbase, ubs, ubr);
+        push_block_banded<J0 + 1, J1>(list, cnt, v, thr, rbase, lim, ubs, ubr);
+    }
+}
 template <int J0, int J1>
 __device__ __forceinline__ void push_block(unsigned long long* list, uint32_t& cnt, const uint32_t (&v)[32], float thr, uint32_t rbase, int lim) {
     if constexpr (J0 < J1) {
@@ -378,6 +412,9 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             // primed threshold: the k-th best score of an already-searched sample of the corpus (rows below
             // tile_begin * 256), a valid lower bound of the final k-th score; ties lose (higher row id)
             float thr = active ? (p.init_thr ? p.init_thr[(size_t)q * p.init_thr_stride] : -FLT_MAX) : INFINITY;
+            const bool banded = p.ub_score != nullptr;
+            const float ubs = (banded && active) ? p.ub_score[q] : 0.0f;
+            const uint32_t ubr = (banded && active) ? p.ub_row[q] : 0u;
             const TileRange tr = class_tiles(p, chunk);
             for (int t = tr.first; t < tr.end; t += tr.stride, iter++) {
                 const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
@@ -419,7 +456,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         const uint32_t rbase = row0 + cb * 32;
                         // rows past the end of the corpus are TMA zero fill: lim masks them (32 = all valid)
                         const int lim = min(32, n_valid - cb * 32);
-                        if (lim == 32) push_block<0, 32>(my_list, cnt, v, thr, rbase, 32);
+                        if (banded) push_block_banded<0, 32>(my_list, cnt, v, thr, rbase, lim, ubs, ubr);
+                        else if (lim == 32) push_block<0, 32>(my_list, cnt, v, thr, rbase, 32);
                         else push_block<0, 32>(my_list, cnt, v, thr, rbase, lim);
                     }
                 }
@@ -565,6 +603,8 @@ int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long
     p.list_set_base = pass.list_set_base;
     p.init_thr = pass.init_thr;
     p.init_thr_stride = pass.init_thr_stride;
+    p.ub_score = pass.ub_score;
+    p.ub_row = pass.ub_row;
     p.n_chunks = plan.n_chunks;
     p.tiles_per_chunk = plan.tiles_per_chunk;
     p.classes_per_slab = plan.classes_per_slab;
