@@ -274,6 +274,8 @@ struct SearchPlan {
     // from all earlier passes (see make_plan)
     int n_passes;
     int tile_b[VQ_MAX_PASSES + 1];
+    int stride[VQ_MAX_PASSES];
+    int ratio;
     vq::TcPlan tc[VQ_MAX_PASSES];
     vq::F32Plan f32[VQ_MAX_PASSES];
     vq::StreamPlan st;
@@ -283,24 +285,31 @@ struct SearchPlan {
     int max_items;
 };
 
-// Threshold-priming pass boundaries (in tiles): [0, first) unprimed, then passes growing by `ratio`, laid out
-// BACKWARDS from the end so that the last pass — the one that does ~94 % of the work — always starts from a
-// threshold computed over 1/(ratio+1) of the corpus and therefore appends only ~ratio * k candidates per query.
-static int pass_schedule(int n_tiles, int first, int ratio, int* tile_b) {
-    int cuts[VQ_MAX_PASSES];
-    int n_cuts = 0;
-    long long b = n_tiles / (ratio + 1);
-    while (n_cuts < VQ_MAX_PASSES - 2 && b > 2LL * first) {
-        cuts[n_cuts++] = (int)b;
-        b /= ratio;
+// Threshold-priming pass schedule (in tiles).  Pass 0 takes every S0-th tile of the corpus (S0 = ratio^m, at most
+// `first_cap` tiles: every row of the unprimed pass becomes a candidate), pass p the multiples of S0 / ratio^p that
+// the sparser passes did not take, the last pass (stride 1) everything that is left: ~(1 - 1/ratio) of the corpus.
+// Every pass therefore samples the WHOLE corpus, so the primed threshold does not depend on the row order (a
+// prefix sample made a corpus sorted by relevance 2.9x slower), and the dominant last pass always starts from a
+// threshold computed over 1/ratio of the rows and appends only ~ratio * k candidates per query.
+// tile_b[] holds cumulative virtual tile counts; stride[] the S_p.
+static int pass_schedule(int n_tiles, int first_cap, int ratio, int* tile_b, int* stride) {
+    int m = 0;
+    long long s0 = 1;
+    while (m < VQ_MAX_PASSES - 1 && (n_tiles + s0 - 1) / s0 > first_cap) {
+        s0 *= ratio;
+        m++;
     }
-    int np = 0;
     tile_b[0] = 0;
-    if (n_cuts > 0 || (long long)first * 4 < n_tiles) tile_b[++np] = first < n_tiles ? first : n_tiles;
-    for (int i = n_cuts - 1; i >= 0; i--)
-        if (cuts[i] > tile_b[np]) tile_b[++np] = cuts[i];
-    if (tile_b[np] < n_tiles || np == 0) tile_b[++np] = n_tiles;
-    return np;
+    long long prev = 0;
+    long long sp = s0;
+    for (int p = 0; p <= m; p++) {
+        const long long c = n_tiles > 0 ? (n_tiles + sp - 1) / sp : 0;  // multiples of sp in [0, n_tiles)
+        stride[p] = (int)sp;
+        tile_b[p + 1] = tile_b[p] + (int)(c - prev);
+        prev = c;
+        sp /= ratio;
+    }
+    return m + 1;
 }
 
 static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
@@ -315,7 +324,8 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
         int first = (idx->n_sms * 2) / m_tiles;
         if (first < 1) first = 1;
         if (first > 56) first = 56;
-        const int np = pass_schedule(n_tiles, first, 8, sp->tile_b);
+        sp->ratio = 8;
+        const int np = pass_schedule(n_tiles, first, sp->ratio, sp->tile_b, sp->stride);
         sp->n_passes = np;
         sp->pass_sets = 0;
         for (int p = 0; p < np; p++) {
@@ -355,7 +365,8 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
             if (first < 1) first = 1;
             if (first > 28) first = 28;  // every row of the first pass becomes a candidate: keep its merge one 8192-key sort
             if (env_first > 0) first = env_first;
-            const int np = pass_schedule(n_tiles, first, ratio, sp->tile_b);
+            sp->ratio = ratio;
+            const int np = pass_schedule(n_tiles, first, ratio, sp->tile_b, sp->stride);
             sp->n_passes = np;
             sp->pass_sets = 0;
             for (int p = 0; p < np; p++) {
@@ -411,9 +422,8 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
     } else if (sp.kind == 1) {
         for (int p = 0; p < sp.n_passes && !rc; p++) {
             const bool last = p == sp.n_passes - 1;
-            vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, p ? thr : nullptr, 1, ub_score, ub_row};
-            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 256;
-            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, rows_end, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, progress, s);
+            vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, 1, ub_score, ub_row};
+            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, progress, s);
             // first pass: every row is a candidate; primed passes add ~ratio * k candidates per query
             const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : 4096;
             if (!rc)
@@ -424,9 +434,8 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
     } else if (sp.kind == 0) {
         for (int p = 0; p < sp.n_passes && !rc; p++) {
             const bool last = p == sp.n_passes - 1;
-            const long long rows_end = last ? ntot : (long long)sp.tile_b[p + 1] * 128;
-            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, rows_end, idx->ld, idx->d, k, sp.f32[p],
-                                     sp.tile_b[p], sp.tile_b[p + 1], p ? thr : nullptr, ub_score, ub_row,
+            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, ntot, idx->ld, idx->d, k, sp.f32[p],
+                                     sp.tile_b[p], sp.tile_b[p + 1], sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, ub_score, ub_row,
                                      lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
             const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 128 + k : 4096;
             if (!rc)

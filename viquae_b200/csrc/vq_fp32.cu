@@ -19,7 +19,8 @@ constexpr int LDS = BM + 4;  // padded row of the k-major smem tiles
 
 __global__ void __launch_bounds__(THREADS, 2)
 f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __restrict__ X, long long n_rows, int ld_x, int d, int k,
-                int m_tiles, int tile_begin, int n_tiles, int n_chunks, int tiles_per_chunk, int nq_pad, const float* __restrict__ init_thr,
+                int m_tiles, int tile_begin, int n_tiles, int map_stride, int map_ratio, int n_chunks, int tiles_per_chunk, int nq_pad,
+                const float* __restrict__ init_thr,
                 const float* __restrict__ ub_score, const uint32_t* __restrict__ ub_row, uint64_t* __restrict__ lists,
                 int* __restrict__ counts) {
     __shared__ __align__(16) float As[2][BK][LDS];  // double-buffered k-major tiles
@@ -54,7 +55,10 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
         const int t0 = tile_begin + chunk * tiles_per_chunk;
         const int t1 = min(n_tiles, t0 + tiles_per_chunk);
         for (int t = t0; t < t1; t++) {
-            const long long x0 = (long long)t * BN;
+            // virtual tile of the pass -> physical corpus tile (every priming pass samples the whole corpus)
+            int jt = t - tile_begin;
+            if (map_ratio) jt = (jt / (map_ratio - 1)) * map_ratio + (jt % (map_ratio - 1)) + 1;
+            const long long x0 = (long long)jt * map_stride * BN;
             float acc[8][8];
 #pragma unroll
             for (int i = 0; i < 8; i++)
@@ -196,11 +200,11 @@ void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan) {
 }
 
 int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
-                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, const float* ub_score,
-                    const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream) {
+                    const F32Plan& plan, int tile_begin, int tile_end, int map_stride, int map_ratio, const float* init_thr,
+                    const float* ub_score, const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream) {
     if (k < 1 || k > VQ_KMAX) return -2;
     if (nq <= 0) return 0;
-    f32::f32_topk_kernel<<<plan.n_ctas, f32::THREADS, 0, stream>>>(q, nq, ld_q, x, n_rows, ld_x, d, k, plan.m_tiles, tile_begin, tile_end,
+    f32::f32_topk_kernel<<<plan.n_ctas, f32::THREADS, 0, stream>>>(q, nq, ld_q, x, n_rows, ld_x, d, k, plan.m_tiles, tile_begin, tile_end, map_stride, map_ratio,
                                                                   plan.n_chunks, plan.tiles_per_chunk, plan.nq_pad, init_thr, ub_score, ub_row, lists, counts);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;

@@ -32,7 +32,11 @@ struct TcParams {
     int* counts;          // [list_sets][nq_pad]
     long long n_rows;
     int nq, nq_pad, k, num_kb, m_tiles, n_tiles, n_chunks, tiles_per_chunk;
-    int tile_begin;       // first corpus tile of this pass (n_tiles is the absolute end)
+    int tile_begin;       // first VIRTUAL tile index of this pass (n_tiles is the virtual end); see map_stride
+    // virtual -> physical tile: j = t - tile_begin; if (map_ratio) j = (j / (map_ratio-1)) * map_ratio + j % (map_ratio-1) + 1;
+    // physical = j * map_stride.  Pass p of the priming schedule takes the multiples of map_stride that the earlier
+    // (sparser) passes did not take, so every pass samples the WHOLE corpus, not a prefix.
+    int map_stride, map_ratio;
     int classes_per_slab;
     int* progress;        // [m_tiles * n_chunks] tile counters of the L2 sharing window (may be null)
     int sync_every, sync_window;
@@ -48,6 +52,7 @@ struct TcParams {
 // one pass over corpus tiles [tile_begin, tile_end): plan must come from tc_plan(nq, (tile_end - tile_begin) * 256 rows)
 struct TcPass {
     int tile_begin, tile_end, list_set_base;
+    int map_stride, map_ratio;
     const float* init_thr;
     int init_thr_stride;
     const float* ub_score;
@@ -64,8 +69,8 @@ struct F32Plan {
 void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan);
 // one pass over corpus tiles (128 rows each) [tile_begin, tile_end); plan from f32_plan(nq, (tile_end - tile_begin) * 128 rows)
 int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
-                    const F32Plan& plan, int tile_begin, int tile_end, const float* init_thr, const float* ub_score,
-                    const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream);
+                    const F32Plan& plan, int tile_begin, int tile_end, int map_stride, int map_ratio, const float* init_thr,
+                    const float* ub_score, const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream);
 
 // ---- K2: small-batch HBM-streaming contraction + fused top-k (vq_stream.cu)
 struct StreamPlan {

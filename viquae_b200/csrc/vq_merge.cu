@@ -11,6 +11,15 @@
 
 namespace vq {
 
+// largest float strictly below x (x finite; -FLT_MAX stays)
+__device__ __forceinline__ float next_below(float x) {
+    if (x == 0.0f) return -1.401298464e-45f;
+    const uint32_t u = __float_as_uint(x);
+    if (x > 0.0f) return __uint_as_float(u - 1);
+    if (x <= -FLT_MAX) return x;
+    return __uint_as_float(u + 1);
+}
+
 constexpr int MERGE_THREADS = 256;
 constexpr int MERGE_WARPS = MERGE_THREADS / 32;
 constexpr int MERGE_CAP_MAX = 8192;  // 64 KB of keys
@@ -135,7 +144,9 @@ merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int u
         for (int r = 0; r < 4; r++) {
             const int e = r * 32 + lane;
             if (e < have) dst[e] = key_to_raw(run[r]);
-            if (e == k - 1 && thr_out) thr_out[q] = total >= k ? key_score(run[r]) : -FLT_MAX;
+            // the next pass samples rows with LOWER ids too, so a score equal to the k-th must still pass its
+            // strict compare: hand out the next float below the k-th score
+            if (e == k - 1 && thr_out) thr_out[q] = total >= k ? next_below(key_score(run[r])) : -FLT_MAX;
             if (out_scores && e < k) {
                 out_scores[(size_t)q * k + e] = e < have ? key_score(run[r]) : -FLT_MAX;
                 out_ids[(size_t)q * k + e] = e < have ? (long long)key_row(run[r]) + id_offset : -1;

@@ -242,6 +242,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // interleave inside it.  With one round of work items cps == G (all clusters sweep the whole pass together);
 // with several rounds each round sweeps its own slab, so every corpus byte is pulled from HBM once.
 struct TileRange { int first, end, stride; };
+// virtual tile index of the pass -> physical corpus tile (see TcParams::map_stride)
+__device__ __forceinline__ int phys_tile(const TcParams& p, int t) {
+    int j = t - p.tile_begin;
+    if (p.map_ratio) j = (j / (p.map_ratio - 1)) * p.map_ratio + (j % (p.map_ratio - 1)) + 1;
+    return j * p.map_stride;
+}
 __device__ __forceinline__ TileRange class_tiles(const TcParams& p, int g) {
     const int s = g / p.classes_per_slab;
     const int c0 = s * p.classes_per_slab;
@@ -343,7 +349,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     }
                 }
                 if (lane == 0) {
-                    const int x_row0 = t * BLOCK_N + (int)rank * C::LOAD_N;
+                    const int x_row0 = phys_tile(p, t) * BLOCK_N + (int)rank * C::LOAD_N;
                     for (int kb = 0; kb < num_kb; kb++) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         tma_load_2d<CG>(&tmap_q, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, q_row0,
@@ -420,7 +426,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                 mbar_wait(&tmem_full_bar[as], aphase);
                 tc_fence_after();
-                const uint32_t row0 = (uint32_t)t * BLOCK_N + half * EPI_COLS;
+                const uint32_t row0 = (uint32_t)phys_tile(p, t) * BLOCK_N + half * EPI_COLS;
                 const int n_valid = (int)min((long long)EPI_COLS, p.n_rows - (long long)row0);  // may be <= 0
                 const uint32_t tcol0 = tmem_base + lane_field + as * BLOCK_N + half * EPI_COLS;
 #pragma unroll 1
@@ -600,6 +606,8 @@ int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long
     p.m_tiles = plan.m_tiles;
     p.n_tiles = pass.tile_end;
     p.tile_begin = pass.tile_begin;
+    p.map_stride = pass.map_stride;
+    p.map_ratio = pass.map_ratio;
     p.list_set_base = pass.list_set_base;
     p.init_thr = pass.init_thr;
     p.init_thr_stride = pass.init_thr_stride;
