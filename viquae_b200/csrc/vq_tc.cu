@@ -3,7 +3,7 @@
 // Replaces faiss IndexFlat(d, METRIC_INNER_PRODUCT)::search as reached from
 // meerqat/ir/search.py:146 -> datasets/search.py:384 for 16-bit corpora.  The score matrix never
 // reaches HBM: every 128(query) x 256(corpus row) tile is accumulated in TMEM by tcgen05.mma
-// (operands staged in shared memory by TMA, 128-byte swizzle), read back with tcgen05.ld by four
+// (operands staged in shared memory by TMA, 128-byte swizzle), read back with tcgen05.ld by eight
 // epilogue warps, and filtered against a per-query running threshold held in a register.
 //
 // Layout of one tile:  D[M = queries, N = corpus rows] = Q[M, K] . X[N, K]^T, both operands K-major.
@@ -19,9 +19,11 @@
 // (warp - 4) / 4).  The epilogue is the critical path next to the MMA: its inner loop is branch-free
 // (predicated 8-byte stores of raw (score, row) pairs through inline PTX).
 //
-// Work decomposition: item = (query tile, residue class g): the item's corpus tiles are
-// g, g + G, g + 2G, ... so that at any moment all clusters work inside a window of ~G tiles and the
-// clusters of different query tiles hit the same corpus tiles in L2.
+// Work decomposition: item = (query tile, residue class g): the item's tiles are g, g + G, g + 2G, ... of
+// the pass (see class_tiles / phys_tile), so that at any moment all clusters work inside a window of ~G
+// tiles; the clusters of different query tiles that share a class are kept within 8 tiles of each other
+// (L2 sharing window in the producer warp) so each corpus tile is pulled from HBM about once.
+// One launch = one pass of the threshold-priming schedule (vq_api.cu: pass_schedule).
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
