@@ -453,3 +453,28 @@ def test_large_k_cross_shard_merge():
     s_m, i_m = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
     cmp = flat_ip.compare_results(s_full.cpu().numpy(), i_full.cpu().numpy(), s_m.cpu().numpy(), i_m.cpu().numpy(), rel_tol=1e-5)
     assert cmp["real_mismatches"] == 0 and cmp["overlap"] == 1.0, cmp
+
+
+def test_lifecycle_no_leak_and_varying_batches():
+    """Create / search / destroy many indexes and alternate batch sizes (workspace regrowth, plan changes):
+    results stay correct and device memory returns to its starting level."""
+    from viquae_b200.index import B200FlatIndex
+    X, Q = make(20000, 300, 128, "bf16", seed=21)
+    Dr, Ir = flat_ip.flat_ip_search(Q, X, 10)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for rep in range(12):
+        idx = B200FlatIndex(d=128, dtype="bf16")
+        idx.add(X)
+        for nq in (1, 300, 17, 129, 64):
+            res = idx.search_batch(Q[:nq], 10)
+            cmp = flat_ip.compare_results(Dr[:nq], Ir[:nq], res.total_scores, res.total_indices, rel_tol=REL_TOL_16)
+            assert cmp["real_mismatches"] == 0, (rep, nq, cmp)
+        s, i = idx.search_tensors(torch.from_numpy(Q).cuda(), 10)
+        assert np.array_equal(i.cpu().numpy()[:, 0], Ir[:, 0])
+        idx.close()
+        del idx, s, i
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 * 2 ** 20, f"device memory leaked: {(free0 - free1) / 2**20:.1f} MiB"
