@@ -10,9 +10,9 @@
 //   wsum             ranx.fuse        fused(d) = sum_r w_r * s'_r(d) over the runs that hold d
 //   result                            union per query sorted by descending fused score (ties: lower id)
 //
-// Three small kernels: A builds the union and the filled [U x R] matrix per query (sort by doc id in
-// shared memory), B reduces the global statistics per run (gzmuv only; fixed-order tree, two-pass
-// variance like np.std), C normalises, combines and sorts.  Latency/HBM-bound and tiny next to K3.
+// Small kernels: A builds the union and the filled [U x R] matrix per query (sort by doc id in shared memory),
+// B1/B2 reduce the global statistics per run (gzmuv only; deterministic: fixed slices, fixed-order trees, Chan's
+// pairwise combination of (n, mean, M2)), C normalises, combines and sorts.  Latency/HBM-bound and tiny next to K3.
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
@@ -173,13 +173,19 @@ union_kernel(const double* __restrict__ scores, const long long* __restrict__ id
     }
 }
 
-// ---- B: global mean / population std per run over all queries (gzmuv)
+// ---- B: global mean / population std per run over all queries (gzmuv), two deterministic stages:
+// B1: block (b, r) reduces its fixed slice of queries to (n, mean, M2 = sum (v - mean)^2) with two passes over its
+//     data (fixed-order tree); B2: one thread per run folds the slices in index order with Chan's pairwise update.
+constexpr int GSTATS_BLOCKS = 96;
+
 __global__ void __launch_bounds__(THREADS)
-gstats_kernel(const double* __restrict__ mat, const int* __restrict__ ucount, int R, int nq, int E, double* __restrict__ gstats) {
+gstats_partial_kernel(const double* __restrict__ mat, const int* __restrict__ ucount, int R, int nq, int E, double* __restrict__ partial) {
     __shared__ double red[THREADS];
-    const int r = blockIdx.x;
+    const int b = blockIdx.x, r = blockIdx.y;
+    const int per = (nq + gridDim.x - 1) / gridDim.x;
+    const int qa = b * per, qb = min(nq, qa + per);
     double s = 0.0, n = 0.0;
-    for (int q = 0; q < nq; q++) {
+    for (int q = qa; q < qb; q++) {
         const int U = ucount[q];
         const double* m = mat + (size_t)q * E * R;
         for (int u = threadIdx.x; u < U; u += THREADS) {
@@ -191,7 +197,7 @@ gstats_kernel(const double* __restrict__ mat, const int* __restrict__ ucount, in
     n = block_sum(n, red);
     const double mean = n > 0.0 ? s / n : 0.0;
     double ss = 0.0;
-    for (int q = 0; q < nq; q++) {
+    for (int q = qa; q < qb; q++) {
         const int U = ucount[q];
         const double* m = mat + (size_t)q * E * R;
         for (int u = threadIdx.x; u < U; u += THREADS) {
@@ -201,9 +207,29 @@ gstats_kernel(const double* __restrict__ mat, const int* __restrict__ ucount, in
     }
     ss = block_sum(ss, red);
     if (threadIdx.x == 0) {
-        gstats[2 * r] = mean;
-        gstats[2 * r + 1] = n > 0.0 ? sqrt(ss / n) : 0.0;
+        double* out = partial + ((size_t)r * gridDim.x + b) * 3;
+        out[0] = n;
+        out[1] = mean;
+        out[2] = ss;
     }
+}
+
+__global__ void gstats_final_kernel(const double* __restrict__ partial, int n_blocks, double* __restrict__ gstats) {
+    const int r = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int b = 0; b < n_blocks; b++) {
+        const double* in = partial + ((size_t)r * n_blocks + b) * 3;
+        const double nb = in[0];
+        if (nb <= 0.0) continue;
+        const double delta = in[1] - mean;
+        const double nt = n + nb;
+        mean += delta * nb / nt;
+        m2 += in[2] + delta * delta * n * nb / nt;
+        n = nt;
+    }
+    gstats[2 * r] = mean;
+    gstats[2 * r + 1] = n > 0.0 ? sqrt(m2 / n) : 0.0;
 }
 
 // ---- C: normalise + weighted sum + sort
@@ -284,7 +310,8 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t fuse_workspace_bytes(int n_runs, int nq, int k_in) {
     const size_t E = (size_t)n_runs * k_in;
     return align256((size_t)nq * E * n_runs * sizeof(double)) + align256((size_t)nq * E * sizeof(long long)) +
-           align256((size_t)nq * sizeof(int)) + align256((size_t)2 * n_runs * sizeof(double));
+           align256((size_t)nq * sizeof(int)) + align256((size_t)2 * n_runs * sizeof(double)) +
+           align256((size_t)3 * n_runs * fuse::GSTATS_BLOCKS * sizeof(double));
 }
 
 int fuse_launch(const double* scores, const long long* ids, const double* weights, const FuseParams& fp,
@@ -302,8 +329,14 @@ int fuse_launch(const double* scores, const long long* ids, const double* weight
     int* ucount = reinterpret_cast<int*>(w);
     w += align256((size_t)nq * sizeof(int));
     double* gstats = reinterpret_cast<double*>(w);
+    w += align256((size_t)2 * R * sizeof(double));
+    double* partial = reinterpret_cast<double*>(w);
     fuse::union_kernel<<<nq, fuse::THREADS, 0, stream>>>(scores, ids, R, nq, k_in, fp.defmin, mat, doc, ucount);
-    if (fp.norm == 2) fuse::gstats_kernel<<<R, fuse::THREADS, 0, stream>>>(mat, ucount, R, nq, E, gstats);
+    if (fp.norm == 2) {
+        const int nb = nq < fuse::GSTATS_BLOCKS ? nq : fuse::GSTATS_BLOCKS;
+        fuse::gstats_partial_kernel<<<dim3(nb, R), fuse::THREADS, 0, stream>>>(mat, ucount, R, nq, E, partial);
+        fuse::gstats_final_kernel<<<R, 32, 0, stream>>>(partial, nb, gstats);
+    }
     fuse::combine_kernel<<<nq, fuse::THREADS, 0, stream>>>(mat, doc, ucount, weights, gstats, R, nq, E, fp.norm, out_scores, out_ids, out_counts);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
