@@ -415,6 +415,41 @@ def test_knowledgebase_save_path_then_load(tmp_path):
                                                                               "metric_type": 0, "load": True, "file": path}})
 
 
+def test_faiss_flat_file_interchange(tmp_path):
+    """An index written in FAISS's "Flat" / "L2norm,Flat" file layout (what the reference's `save_path` leaves on
+    disk, meerqat/ir/search.py:246-248) loads through `load: true` and searches like the index it came from."""
+    from viquae_b200 import faiss_io
+    from viquae_b200.index import B200FlatIndex
+    from viquae_b200.search import KnowledgeBase
+    rng = np.random.default_rng(21)
+    emb = rng.standard_normal((1500, 48)).astype(np.float32)
+    q = rng.standard_normal((17, 48)).astype(np.float32)
+    for factory in ("Flat", "L2norm,Flat"):
+        src = B200FlatIndex(dtype="f32", string_factory=factory)
+        src.add(emb)
+        path = tmp_path / (factory.replace(",", "_") + ".faiss")
+        faiss_io.save_faiss_flat(src, path)
+        ff = faiss_io.read_flat_index(path)
+        assert ff.string_factory == factory and ff.rows.shape == emb.shape
+        if factory == "Flat":
+            assert np.array_equal(ff.rows, emb)
+        else:
+            np.testing.assert_allclose(np.linalg.norm(ff.rows, axis=1), 1.0, rtol=1e-6)
+
+        class DictDS(dict):
+            def __len__(self):
+                return len(next(iter(self.values())))
+        kb = KnowledgeBase(dataset=DictDS({"e": emb}), index_kwargs={"x": {"column": "e", "key": "q", "string_factory": factory, "metric_type": 0,
+                                                                           "dtype": "f32", "load": True, "file": str(path)}})
+        assert kb.indexes["x"].do_L2norm is (factory != "Flat")
+        s1, i1 = src.search_batch(q, k=20)
+        s2, i2 = kb.search_batch("x", q, k=20)
+        assert np.array_equal(np.asarray(i1), np.asarray(i2)) and np.array_equal(np.asarray(s1), np.asarray(s2))
+    faiss_io.write_flat_index(tmp_path / "l2.faiss", emb, metric_type=1)
+    with pytest.raises(ValueError, match="inner-product only"):
+        B200FlatIndex.load(tmp_path / "l2.faiss")
+
+
 @pytest.mark.parametrize("dtype,N,nq,d,k", [("bf16", 30000, 140, 256, 129), ("bf16", 50000, 40, 768, 1000), ("f16", 3000, 9, 64, 300),
                                             ("f32", 6000, 33, 96, 500), ("bf16", 700, 5, 32, 2048), ("bf16", 300000, 260, 128, 257)])
 def test_large_k_banded_rounds(dtype, N, nq, d, k):
@@ -478,3 +513,22 @@ def test_lifecycle_no_leak_and_varying_batches():
     torch.cuda.empty_cache()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 64 * 2 ** 20, f"device memory leaked: {(free0 - free1) / 2**20:.1f} MiB"
+
+
+def test_cuda_graph_replay_equals_direct_search():
+    """The whole multi-pass search is capture-safe (no host sync, no allocation): a CUDA-graph replay returns
+    exactly what a direct call returns, for new queries written into the static input, and refuses a grown index."""
+    from viquae_b200.index import B200FlatIndex
+    X, Q = make(40000, 7, 128, "bf16", seed=31)
+    idx = B200FlatIndex(d=128, dtype="bf16")
+    idx.add(torch.from_numpy(X).cuda())
+    cap = idx.capture_search(7, 50)
+    for seed in (1, 2, 3):
+        q = torch.from_numpy(make(8, 7, 128, "bf16", seed=seed)[1]).cuda()
+        s0, i0 = idx.search_tensors(q, 50)
+        s1, i1 = cap(q)
+        torch.cuda.synchronize()
+        assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    idx.add(torch.from_numpy(X[:10]).cuda())
+    with pytest.raises(RuntimeError, match="capture again"):
+        cap.replay()

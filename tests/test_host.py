@@ -149,3 +149,45 @@ def test_arrow_column_blocks_zero_copy_and_fallback():
     assert np.array_equal(np.concatenate(list(arrow_column_blocks(sub, "emb"))), x[[5, 3, 900]])
     ds64 = datasets.Dataset.from_dict({"emb": x.astype(np.float64).tolist()})
     assert np.allclose(np.concatenate(list(arrow_column_blocks(ds64, "emb"))), x)
+
+
+def test_faiss_flat_file_layout(tmp_path):
+    """The FAISS "Flat" / "L2norm,Flat" file layout restated in viquae_b200/faiss_io.py (faiss is absent: the
+    expected bytes are assembled by hand from the layout table in that module's header — parity unpinned)."""
+    import struct
+    from viquae_b200 import faiss_io
+    rows = np.arange(12, dtype=np.float32).reshape(3, 4) / 7
+    header = struct.pack("<i", 4) + struct.pack("<q", 3) + struct.pack("<q", 1 << 20) * 2 + b"\x01" + struct.pack("<i", 0)
+    flat = b"IxFI" + header + struct.pack("<Q", 12) + rows.tobytes()
+    p = tmp_path / "flat.faiss"
+    faiss_io.write_flat_index(p, rows)
+    assert p.read_bytes() == flat
+    got = faiss_io.read_flat_index(p)
+    assert got.l2norm is False and got.metric_type == 0 and got.string_factory == "Flat"
+    np.testing.assert_array_equal(got.rows, rows)
+
+    pre = b"IxPT" + header + struct.pack("<i", 1) + b"VNrm" + struct.pack("<f", 2.0) + struct.pack("<ii", 4, 4) + b"\x01" + flat
+    p2 = tmp_path / "l2norm_flat.faiss"
+    faiss_io.write_flat_index(p2, rows, l2norm=True)
+    assert p2.read_bytes() == pre
+    got = faiss_io.read_flat_index(p2)
+    assert got.l2norm is True and got.string_factory == "L2norm,Flat"
+    np.testing.assert_array_equal(got.rows, rows)
+
+    # empty index, L2 metric fourcc, and the failure modes
+    faiss_io.write_flat_index(tmp_path / "empty", np.zeros((0, 8), np.float32))
+    assert faiss_io.read_flat_index(tmp_path / "empty").rows.shape == (0, 8)
+    faiss_io.write_flat_index(tmp_path / "l2", rows, metric_type=1)
+    assert (tmp_path / "l2").read_bytes()[:4] == b"IxF2" and faiss_io.read_flat_index(tmp_path / "l2").metric_type == 1
+    (tmp_path / "ivf").write_bytes(b"IwFl" + header)
+    with pytest.raises(NotImplementedError):
+        faiss_io.read_flat_index(tmp_path / "ivf")
+    (tmp_path / "cut").write_bytes(flat[:-5])
+    with pytest.raises(ValueError, match="truncated"):
+        faiss_io.read_flat_index(tmp_path / "cut")
+    (tmp_path / "bad").write_bytes(b"IxFI" + header + struct.pack("<Q", 11) + rows.tobytes())
+    with pytest.raises(ValueError):
+        faiss_io.read_flat_index(tmp_path / "bad")
+    (tmp_path / "pca").write_bytes(b"IxPT" + header + struct.pack("<i", 1) + b"PcAm")
+    with pytest.raises(NotImplementedError):
+        faiss_io.read_flat_index(tmp_path / "pca")

@@ -98,41 +98,85 @@ merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int u
                    int cap) {
     extern __shared__ uint64_t keys[];           // [cap] gathered keys, then [8][128] for the tree
     __shared__ int off_s[MERGE_MAX_SETS + 2];     // exclusive prefix sums of the list lengths (index 0 = set 0)
+    __shared__ int warp_tot[MERGE_WARPS];
     __shared__ int round_end;
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = n_sets + 1;  // logical list l: 0 = running merged list (set 0), l >= 1 = set_begin + l - 1
-    for (int l = threadIdx.x; l < L; l += MERGE_THREADS) {
-        const int set = l == 0 ? 0 : set_begin + l - 1;
-        off_s[l + 1] = (l == 0 && !use_set0) ? 0 : counts[(size_t)set * nq_pad + q];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        off_s[0] = 0;
-        for (int l = 1; l <= L; l++) { run += off_s[l]; off_s[l] = run; }
+    // exclusive prefix sums of the list lengths, in parallel: thread t owns lists [t*PER, t*PER + PER)
+    constexpr int PER = (MERGE_MAX_SETS + MERGE_THREADS) / MERGE_THREADS;
+    {
+        int c[PER], mine = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const int l = threadIdx.x * PER + j;
+            const int set = l == 0 ? 0 : set_begin + l - 1;
+            c[j] = (l >= L || (l == 0 && !use_set0)) ? 0 : __ldcg(counts + (size_t)set * nq_pad + q);
+        }
+#pragma unroll
+        for (int j = 0; j < PER; j++) mine += c[j];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(VQ_FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int before = incl - mine;
+#pragma unroll
+        for (int w = 0; w < MERGE_WARPS; w++) before += w < warp ? warp_tot[w] : 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const int l = threadIdx.x * PER + j;
+            if (l <= L) off_s[l] = before;
+            before += c[j];
+        }
     }
     __syncthreads();
     const int total = off_s[L];
     uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
     int l0 = 0;
     while (l0 < L) {
-        if (threadIdx.x == 0) {  // this round: as many whole lists as fit in the gather buffer
-            int l1 = l0;
-            while (l1 < L && off_s[l1 + 1] - off_s[l0] <= cap) l1++;
-            round_end = l1;
+        int l1 = L;
+        if (total > cap) {  // several rounds: as many whole lists as fit in the gather buffer
+            if (threadIdx.x == 0) {
+                int e = l0;
+                while (e < L && off_s[e + 1] - off_s[l0] <= cap) e++;
+                round_end = e;
+            }
+            __syncthreads();
+            l1 = round_end;
         }
-        __syncthreads();
-        const int l1 = round_end;
         const int base = off_s[l0];
-        for (int l = l0 + warp; l < l1; l += MERGE_WARPS) {
-            const int set = l == 0 ? 0 : set_begin + l - 1;
-            const int n = off_s[l + 1] - off_s[l];
-            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(lists + ((size_t)set * nq_pad + q) * VQ_CAP);
-            for (int i = lane; i < n; i += 32) keys[off_s[l] - base + i] = raw_to_key(__ldcg(src + i));
+        const int n_round = off_s[l1] - base;
+        // flat gather: element i of the round lives in the list l with off_s[l] <= base + i < off_s[l + 1]; four
+        // independent loads in flight per thread (this kernel is latency-bound at small query counts)
+        for (int i0 = threadIdx.x; i0 < n_round; i0 += 4 * MERGE_THREADS) {
+            unsigned long long raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * MERGE_THREADS;
+                raw[u] = 0ull;
+                if (i < n_round) {
+                    const int x = base + i;
+                    int lo = l0, hi = l1;  // invariant: off_s[lo] <= x < off_s[hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (off_s[mid] <= x) lo = mid; else hi = mid;
+                    }
+                    const int set = lo == 0 ? 0 : set_begin + lo - 1;
+                    raw[u] = __ldcg(reinterpret_cast<const unsigned long long*>(lists + ((size_t)set * nq_pad + q) * VQ_CAP) + (x - off_s[lo]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * MERGE_THREADS;
+                if (i < n_round) keys[i] = raw_to_key(raw[u]);
+            }
         }
         __syncthreads();
-        fold_chunks(keys, off_s[l1] - base, run, warp, lane);
+        fold_chunks(keys, n_round, run, warp, lane);
         __syncthreads();
         l0 = l1;
     }

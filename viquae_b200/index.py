@@ -262,6 +262,13 @@ class B200FlatIndex(BaseIndex):
                                        ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         return scores, ids
 
+    def capture_search(self, nq: int, k: int = 100, query_dtype=None, l2norm: Optional[bool] = None) -> "CapturedSearch":
+        """Records one ``search_tensors`` call of a fixed shape into a CUDA graph (every launch of the search is
+        asynchronous on the caller's stream and touches only preallocated memory, so the whole multi-pass
+        sequence replays as one submission).  For the latency regime (BASELINE config 5: batch 1-32 per call,
+        interact/system.py's one-question loop).  The index must not grow while the graph is alive."""
+        return CapturedSearch(self, nq, k, query_dtype, l2norm)
+
     def search_batch(self, queries, k: int = 10, **kwargs) -> BatchedSearchResults:
         """``FaissIndex.search_batch`` (datasets/search.py:369-385): numpy float32 [nq, d] in,
         (float32 [nq, k], int64 [nq, k]) numpy out through the host-buffer C-ABI call."""
@@ -315,8 +322,15 @@ class B200FlatIndex(BaseIndex):
                        "string_factory": self.string_factory, "id_offset": self.id_offset}, f)
 
     @classmethod
-    def load(cls, file, device: int = 0, storage_options=None, variant: Optional[str] = None) -> "B200FlatIndex":
+    def load(cls, file, device: int = 0, storage_options=None, variant: Optional[str] = None, dtype: str = "bf16") -> "B200FlatIndex":
+        """Loads an index written by :meth:`save`, or a FAISS "Flat" / "L2norm,Flat" file written by the
+        reference's ``save_path`` (``faiss.write_index``; recognised by its fourcc, stored as ``dtype``)."""
         file = os.fspath(file)
+        with open(file, "rb") as f:
+            magic = f.read(4)
+        if magic in (b"IxFI", b"IxF2", b"IxFl", b"IxPT"):
+            from .faiss_io import load_faiss_flat as _load
+            return _load(file, dtype=dtype, device=device, variant=variant)
         with open(file, "rt") as f:
             hdr = json.load(f)
         if hdr.get("format") != "viquae_b200.flat_ip.v1":
@@ -331,6 +345,58 @@ class B200FlatIndex(BaseIndex):
             rows = np.ascontiguousarray(rows)
             _lib.check(_lib.load().vq_index_add(idx._h, rows.ctypes.data, rows.shape[0], code, 0, None))
         return idx
+
+
+class CapturedSearch:
+    """A fixed-shape search held as a CUDA graph: write ``queries`` (or pass them to :meth:`__call__`), replay,
+    read ``scores`` / ``ids``.  All three are static device tensors owned by this object."""
+
+    def __init__(self, index: B200FlatIndex, nq: int, k: int, query_dtype=None, l2norm: Optional[bool] = None):
+        torch = _torch()
+        if index._h is None or index.ntotal == 0:
+            raise RuntimeError("empty index: add vectors first")
+        if nq < 1:
+            raise ValueError("nq must be >= 1")
+        self.index, self.nq, self.k = index, nq, k
+        self.ntotal = index.ntotal
+        dev = f"cuda:{index.device}"
+        self.queries = torch.zeros((nq, index.d), dtype=query_dtype or torch.float32, device=dev)
+        self.scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        self.ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        # own workspace: the index's shared scratch buffer may be reallocated by a later, larger search
+        self._ws = torch.empty((_lib.load().vq_index_workspace_bytes(index._h, nq, k),), dtype=torch.uint8, device=dev)
+        self._l2 = int(index.do_L2norm if l2norm is None else bool(l2norm))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(index.device))
+        with torch.cuda.stream(side):
+            self._launch(side)  # warm-up outside capture: one-time function attributes, lazy module load
+        torch.cuda.current_stream(index.device).wait_stream(side)
+        side.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._launch(torch.cuda.current_stream(index.device))
+
+    def _launch(self, stream):
+        q = self.queries
+        _lib.check(_lib.load().vq_index_search(self.index._h, q.data_ptr(), self.nq, _tensor_dtype_code(q), self._l2, self.k,
+                                               self.scores.data_ptr(), self.ids.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                               stream.cuda_stream))
+
+    def replay(self):
+        if self.index._h is None or self.index.ntotal != self.ntotal:
+            raise RuntimeError("the index changed after capture_search(); capture again")
+        self.graph.replay()
+        return self.scores, self.ids
+
+    def __call__(self, queries):
+        self.queries.copy_(queries, non_blocking=True)
+        return self.replay()
+
+
+def load_faiss_flat(file, dtype: str = "bf16", device: int = 0, variant: Optional[str] = None) -> B200FlatIndex:
+    """``faiss.read_index`` for "Flat" / "L2norm,Flat" files (see :mod:`viquae_b200.faiss_io`)."""
+    from .faiss_io import load_faiss_flat as _load
+    return _load(file, dtype=dtype, device=device, variant=variant)
 
 
 def merge_topk(scores, ids, k_out: Optional[int] = None):

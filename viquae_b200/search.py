@@ -144,7 +144,7 @@ class KnowledgeBase:
             path = file or save_path
             if path is None:
                 raise ValueError("load=True needs `file` (or `save_path`) pointing at a saved index")
-            engine = B200FlatIndex.load(path, device=dev, variant=variant)
+            engine = B200FlatIndex.load(path, device=dev, variant=variant, dtype=dtype)
             if self.dataset is not None and len(engine) != len(self.dataset):
                 raise ValueError(f"Index size should match Dataset size, but Index '{index_name}' at {path} has "
                                  f"{len(engine)} elements while the dataset has {len(self.dataset)} examples.")
