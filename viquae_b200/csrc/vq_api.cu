@@ -7,6 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
@@ -35,6 +38,13 @@ struct vq_index {
     // engine-owned buffers of the host-buffer entry point
     void* hws;
     size_t hws_bytes;
+    // host ingest pipeline: two pinned buffers + two device staging buffers, filled alternately (allocated at the
+    // first host-side add, kept for the index's lifetime)
+    void* pin[2];
+    void* stage[2];
+    cudaEvent_t ingest_ev[2];
+    int ingest_ev_ok[2];
+    size_t ingest_bytes;
     // measurement support: CUDA events around the dominant kernel of each search
     int timing;
     int n_timed;
@@ -45,6 +55,61 @@ struct vq_index {
 static size_t esize(int dtype) { return dtype == VQ_F32 ? 4 : 2; }
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static bool dtype_ok(int t) { return t == VQ_F32 || t == VQ_BF16 || t == VQ_F16; }
+
+constexpr size_t VQ_INGEST_CHUNK = 32ull << 20;  // per pipeline stage
+
+static void ingest_release(vq_index* idx) {
+    for (int b = 0; b < 2; b++) {
+        if (idx->pin[b]) cudaFreeHost(idx->pin[b]);
+        if (idx->stage[b]) cudaFree(idx->stage[b]);
+        if (idx->ingest_ev_ok[b]) cudaEventDestroy(idx->ingest_ev[b]);
+        idx->pin[b] = idx->stage[b] = nullptr;
+        idx->ingest_ev_ok[b] = 0;
+    }
+    idx->ingest_bytes = 0;
+}
+
+static cudaError_t ingest_reserve(vq_index* idx, size_t bytes) {
+    if (idx->ingest_bytes >= bytes) return cudaSuccess;
+    ingest_release(idx);
+    for (int b = 0; b < 2; b++) {
+        cudaError_t e = cudaHostAlloc(&idx->pin[b], bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc(&idx->stage[b], bytes);
+        if (e == cudaSuccess) {
+            e = cudaEventCreateWithFlags(&idx->ingest_ev[b], cudaEventDisableTiming);
+            idx->ingest_ev_ok[b] = e == cudaSuccess;
+        }
+        if (e != cudaSuccess) {
+            ingest_release(idx);
+            return e;
+        }
+    }
+    idx->ingest_bytes = bytes;
+    return cudaSuccess;
+}
+
+// pageable -> pinned copy on several host threads (one memcpy stream per thread saturates ~1/4 of a socket)
+static void host_copy(void* dst, const void* src, size_t bytes) {
+    static const unsigned n_threads = [] {
+        unsigned h = std::thread::hardware_concurrency();
+        unsigned n = h / 2;
+        return n < 1 ? 1u : (n > 8 ? 8u : n);
+    }();
+    if (bytes < (4u << 20) || n_threads == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes / n_threads) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; t++) {
+        const size_t a = (size_t)t * per;
+        if (a >= bytes) break;
+        const size_t len = bytes - a < per ? bytes - a : per;
+        pool.emplace_back([=] { memcpy((uint8_t*)dst + a, (const uint8_t*)src + a, len); });
+    }
+    memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto& th : pool) th.join();
+}
 
 extern "C" {
 
@@ -103,6 +168,7 @@ void vq_index_destroy(vq_index* idx) {
     cudaSetDevice(idx->device);
     if (idx->data) cudaFree(idx->data);
     if (idx->hws) cudaFree(idx->hws);
+    ingest_release(idx);
     if (idx->timing)
         for (int i = 0; i < VQ_TIMING_SLOTS; i++) {
             cudaEventDestroy(idx->ev0[i]);
@@ -209,26 +275,32 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
         rc = vq::prep_rows_launch(x, src_dtype, idx->d, dst, idx->dtype, idx->ld, (long long)n, idx->d, l2norm, s);
         if (rc) return fail(VQ_ERR_CUDA, "vq_index_add: prep kernel launch failed (%d)", rc);
     } else {
-        // host source: stage through a device buffer in 64 MB pieces, convert on the device
+        // host source: pageable rows -> pinned buffer (host threads) -> device staging (DMA) -> conversion kernel,
+        // double-buffered so the host copy of chunk c+1 overlaps the DMA and kernel of chunk c
         const size_t src_row = (size_t)idx->d * esize(src_dtype);
-        uint64_t chunk = (64ull << 20) / src_row;
+        uint64_t chunk = VQ_INGEST_CHUNK / src_row;
         if (chunk < 1) chunk = 1;
-        if (chunk > n) chunk = n;
-        void* stage = nullptr;
-        CUDA_TRY(cudaMalloc(&stage, chunk * src_row));
-        for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+        cudaError_t e = ingest_reserve(idx, chunk * src_row);
+        if (e != cudaSuccess) return fail(VQ_ERR_NOMEM, "vq_index_add: ingest buffers: %s", cudaGetErrorString(e));
+        uint64_t c = 0;
+        for (uint64_t r0 = 0; r0 < n; r0 += chunk, c++) {
             const uint64_t m = (n - r0 < chunk) ? n - r0 : chunk;
-            cudaError_t e = cudaMemcpyAsync(stage, (const uint8_t*)x + r0 * src_row, m * src_row, cudaMemcpyHostToDevice, s);
+            const int b = (int)(c & 1);
+            if (c >= 2) e = cudaEventSynchronize(idx->ingest_ev[b]);  // chunk c-2 has left this stage
             if (e == cudaSuccess) {
-                rc = vq::prep_rows_launch(stage, src_dtype, idx->d, dst + r0 * row, idx->dtype, idx->ld, (long long)m, idx->d, l2norm, s);
-                if (rc == 0) e = cudaStreamSynchronize(s);
+                host_copy(idx->pin[b], (const uint8_t*)x + r0 * src_row, m * src_row);
+                e = cudaMemcpyAsync(idx->stage[b], idx->pin[b], m * src_row, cudaMemcpyHostToDevice, s);
+            }
+            if (e == cudaSuccess) {
+                rc = vq::prep_rows_launch(idx->stage[b], src_dtype, idx->d, dst + r0 * row, idx->dtype, idx->ld, (long long)m, idx->d, l2norm, s);
+                if (rc == 0) e = cudaEventRecord(idx->ingest_ev[b], s);
             }
             if (e != cudaSuccess || rc) {
-                cudaFree(stage);
+                cudaStreamSynchronize(s);
                 return fail(VQ_ERR_CUDA, "vq_index_add: host staging failed: %s (%d)", cudaGetErrorString(e), rc);
             }
         }
-        cudaFree(stage);
+        CUDA_TRY(cudaStreamSynchronize(s));  // the caller may free x; the staging buffers are reused by the next call
     }
     idx->ntotal += n;
     return VQ_OK;
