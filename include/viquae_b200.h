@@ -26,6 +26,11 @@ extern "C" {
 #define VQ_F32 0
 #define VQ_BF16 1
 #define VQ_F16 2
+/* storage type only (vq_index_create): every fp32 value kept as three bf16 terms hi + mid + lo (exactly the fp32
+ * value), contracted on the tensor cores as hi*hi + hi*mid + mid*hi + mid*mid + hi*lo + lo*hi with fp32
+ * accumulation: fp32-faithful scores (the dropped terms are below 2^-24 of a product) at tensor-core speed.
+ * 12 bytes per element on the device.  Stands in for the fp32 sgemm FAISS runs (datasets/search.py:384). */
+#define VQ_F32X3 3
 
 /* error codes */
 #define VQ_OK 0
@@ -48,8 +53,8 @@ const char* vq_last_error(void);
 const char* vq_version(void);
 
 /* faiss.IndexFlat(d, faiss.METRIC_INNER_PRODUCT)            [datasets/search.py:276-288]
- * `dtype` is the STORAGE type of the corpus on the device (VQ_F32 = exact mode, VQ_BF16 / VQ_F16 =
- * tensor-core mode); `capacity` pre-sizes the device buffer in rows (it grows on demand). */
+ * `dtype` is the STORAGE type of the corpus on the device (VQ_F32 = exact fixed-order mode, VQ_BF16 / VQ_F16 =
+ * tensor-core mode on rounded embeddings, VQ_F32X3 = tensor-core mode on split fp32 embeddings); `capacity` pre-sizes the device buffer in rows (it grows on demand). */
 int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capacity);
 void vq_index_destroy(vq_index* idx);
 

@@ -532,3 +532,71 @@ def test_cuda_graph_replay_equals_direct_search():
     idx.add(torch.from_numpy(X[:10]).cuda())
     with pytest.raises(RuntimeError, match="capture again"):
         cap.replay()
+
+
+REL_TOL_F32X3 = 1e-5  # north star for the fp32 mode: scores within 1e-5 relative of the fp32 reference (measured: <= 3.3e-6, typically 6e-7)
+
+
+@pytest.mark.parametrize("N,nq,d,k,dist,factory", [
+    (5000, 70, 768, 100, "normal", "Flat"),
+    (70001, 300, 768, 100, "normal", "Flat"),        # cta_group::2, several priming passes
+    (40000, 130, 768, 100, "dpr", "Flat"),           # DPR-like: scores cluster near 71 +- 2, all products positive
+    (30000, 40, 512, 100, "normal", "L2norm,Flat"),  # CLIP/ArcFace regime, scores in [-1, 1]
+    (9000, 33, 100, 7, "normal", "Flat"),            # d not a multiple of 8: zero-padded segments
+    (50, 3, 24, 100, "normal", "Flat"),              # N < k: -1 padding
+    (30000, 20, 256, 300, "normal", "Flat"),         # k > 128: banded rounds
+])
+def test_f32x3_split_operand_mode_is_fp32_faithful(N, nq, d, k, dist, factory):
+    """dtype="f32x3": fp32 embeddings as three bf16 terms, six tensor-core product terms, fp32 accumulation.
+    Against the fp32 fixed-order oracle on the SAME fp32 inputs: scores within 1e-5 relative, ids identical
+    except where two scores are closer than that (FAISS's own sgemm is no closer to the fixed-order sum)."""
+    X, Q = make(N, nq, d, "f32", seed=17, dist=dist)
+    X, Q = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Q, np.float32)  # the DPR-like family comes out as float64
+    idx = engine(X, "f32x3", string_factory=factory)
+    res = idx.search_batch(Q, k)
+    D, I = np.asarray(res.total_scores), np.asarray(res.total_indices)
+    if factory != "Flat":  # the oracle gets the engine's own normalised fp32 rows (same arithmetic as the f32 index)
+        Xn = idx.reconstruct_n(0, None, "f32")
+        ref = engine(X, "f32", string_factory=factory)
+        assert np.array_equal(Xn.view(np.uint32), ref.reconstruct_n(0, None, "f32").view(np.uint32)), "split + join must be exact"
+        Qn = Q / np.linalg.norm(Q, axis=1, keepdims=True)
+        Dr, Ir = c_oracle.flat_ip(Qn.astype(np.float32), Xn, k)
+        tol = REL_TOL_F32X3  # (the query normalisation also differs in the last bit between numpy and the device)
+    else:
+        assert np.array_equal(idx.reconstruct_n(0, None, "f32").view(np.uint32), X.view(np.uint32)), "split + join must be exact"
+        Dr, Ir = c_oracle.flat_ip(Q, X, k)
+        tol = REL_TOL_F32X3
+    kk = min(k, N)
+    floor = 1.0 if factory != "Flat" else float(np.sqrt(d))  # one standard deviation of a score: keeps near-zero scores meaningful
+    # ids: the two top-k sets may differ only by rows whose score is within the tolerance of the k-th score (another
+    # summation order swaps near-ties; FAISS's blocked sgemm would too)
+    cmp = flat_ip.compare_results(Dr, Ir, D, I, rel_tol=tol, abs_tol=tol * floor)
+    assert cmp["real_mismatches"] == 0 and cmp["overlap"] >= 0.995, cmp
+    # scores, rank by rank (a swap of two near-equal neighbours leaves the sorted score lists within the tolerance)
+    valid = Ir >= 0
+    err = np.abs(D.astype(np.float64) - Dr) / np.maximum(np.abs(Dr), floor)
+    assert float(err[valid].max()) <= tol, float(err[valid].max())
+    # and every returned (id, score) pair is that row's true inner product
+    Xs = idx.reconstruct_n(0, None, "f32").astype(np.float64)
+    Qs = (Q / np.linalg.norm(Q, axis=1, keepdims=True) if factory != "Flat" else Q).astype(np.float64)
+    got = I >= 0
+    truth = np.einsum("qkd,qd->qk", Xs[np.where(got, I, 0)], Qs)
+    err = np.abs(D - truth) / np.maximum(np.abs(truth), floor)
+    assert float(err[got].max()) <= tol, float(err[got].max())
+    assert np.array_equal(got, valid) and np.all(I[:, kk:] == -1) and np.all(np.diff(D[:, :kk], axis=1) <= 0)
+
+
+def test_f32x3_save_load_and_device_queries(tmp_path):
+    from viquae_b200.index import B200FlatIndex
+    X, Q = make(3000, 9, 72, "f32", seed=23)
+    idx = engine(X, "f32x3")
+    path = str(tmp_path / "x3.index")
+    idx.save(path)
+    back = B200FlatIndex.load(path)
+    assert back.dtype == "f32x3" and len(back) == 3000
+    s0, i0 = idx.search_tensors(torch.from_numpy(Q).cuda(), 20)
+    s1, i1 = back.search_tensors(torch.from_numpy(Q).cuda().to(torch.bfloat16).float(), 20)  # other query values: just runs
+    s2, i2 = back.search_tensors(torch.from_numpy(Q).cuda(), 20)
+    assert torch.equal(i0, i2) and torch.equal(s0, s2)
+    with pytest.raises(ValueError):
+        idx.reconstruct_n(0, None, "f32x3")

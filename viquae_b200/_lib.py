@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libviquae_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
+F32X3 = 3  # storage only: fp32 values split into three bf16 terms, tensor-core contraction at fp32 fidelity
 VARIANT_AUTO, VARIANT_TC_CG1, VARIANT_TC_CG2, VARIANT_STREAM = 0, 1, 2, 3
 ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4
 

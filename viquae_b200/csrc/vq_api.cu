@@ -32,6 +32,7 @@ static int fail(int code, const char* fmt, ...) {
 
 struct vq_index {
     int d, dtype, device, ld, n_sms, variant;
+    int kd, kdtype, seg;  // what the kernels contract over: kd columns of kdtype (VQ_F32X3: 6 segments of seg bf16 columns)
     uint64_t capacity, ntotal;
     int64_t id_offset;
     void* data;
@@ -52,9 +53,10 @@ struct vq_index {
     cudaEvent_t ev0[VQ_TIMING_SLOTS], ev1[VQ_TIMING_SLOTS];
 };
 
-static size_t esize(int dtype) { return dtype == VQ_F32 ? 4 : 2; }
+static size_t esize(int dtype) { return dtype == VQ_F32 ? 4 : 2; }  // of one stored element (VQ_F32X3 stores bf16)
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-static bool dtype_ok(int t) { return t == VQ_F32 || t == VQ_BF16 || t == VQ_F16; }
+static bool dtype_ok(int t) { return t == VQ_F32 || t == VQ_BF16 || t == VQ_F16; }  // of vectors crossing the ABI
+static bool storage_ok(int t) { return dtype_ok(t) || t == VQ_F32X3; }
 
 constexpr size_t VQ_INGEST_CHUNK = 32ull << 20;  // per pipeline stage
 
@@ -111,6 +113,18 @@ static void host_copy(void* dst, const void* src, size_t bytes) {
     for (auto& th : pool) th.join();
 }
 
+// [n, d] rows of src_dtype -> the index's storage layout (corpus rows, or the query-side arrangement of VQ_F32X3)
+static int to_storage(const vq_index* idx, const void* src, int src_dtype, void* dst, long long n, int l2norm, int query_side, cudaStream_t s) {
+    if (idx->dtype == VQ_F32X3) return vq::split_rows_launch(src, src_dtype, idx->d, dst, idx->seg, n, idx->d, l2norm, query_side, s);
+    return vq::prep_rows_launch(src, src_dtype, idx->d, dst, idx->dtype, idx->ld, n, idx->d, l2norm, s);
+}
+
+// stored corpus rows -> [n, d] rows of dst_dtype
+static int from_storage(const vq_index* idx, const void* src, void* dst, int dst_dtype, long long n, cudaStream_t s) {
+    if (idx->dtype == VQ_F32X3) return vq::join_rows_launch(src, idx->seg, dst, dst_dtype, idx->d, n, idx->d, s);
+    return vq::prep_rows_launch(src, idx->dtype, idx->ld, dst, dst_dtype, idx->d, n, idx->d, 0, s);
+}
+
 extern "C" {
 
 const char* vq_last_error(void) { return g_err; }
@@ -127,7 +141,7 @@ int vq_device_count(void) {
 }
 
 int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capacity) {
-    if (!out || d <= 0 || !dtype_ok(dtype)) return fail(VQ_ERR_INVALID, "vq_index_create: bad arguments (d=%d dtype=%d)", d, dtype);
+    if (!out || d <= 0 || !storage_ok(dtype)) return fail(VQ_ERR_INVALID, "vq_index_create: bad arguments (d=%d dtype=%d)", d, dtype);
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(VQ_ERR_INVALID, "vq_index_create: device %d not in [0, %d)", device, ndev);
@@ -140,6 +154,14 @@ int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capac
     idx->dtype = dtype;
     idx->device = device;
     idx->ld = dtype == VQ_F32 ? (d + 3) / 4 * 4 : (d + 7) / 8 * 8;  // 16-byte row stride (float4 / TMA)
+    idx->kd = d;
+    idx->kdtype = dtype;
+    idx->seg = 0;
+    if (dtype == VQ_F32X3) {
+        idx->seg = (d + 7) / 8 * 8;
+        idx->ld = idx->kd = 6 * idx->seg;
+        idx->kdtype = VQ_BF16;
+    }
     idx->n_sms = prop.multiProcessorCount;
     idx->variant = VQ_VARIANT_AUTO;
     idx->capacity = 0;
@@ -272,7 +294,7 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
     const size_t row = (size_t)idx->ld * esize(idx->dtype);
     uint8_t* dst = (uint8_t*)idx->data + idx->ntotal * row;
     if (is_device_ptr(x)) {
-        rc = vq::prep_rows_launch(x, src_dtype, idx->d, dst, idx->dtype, idx->ld, (long long)n, idx->d, l2norm, s);
+        rc = to_storage(idx, x, src_dtype, dst, (long long)n, l2norm, 0, s);
         if (rc) return fail(VQ_ERR_CUDA, "vq_index_add: prep kernel launch failed (%d)", rc);
     } else {
         // host source: pageable rows -> pinned buffer (host threads) -> device staging (DMA) -> conversion kernel,
@@ -292,7 +314,7 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
                 e = cudaMemcpyAsync(idx->stage[b], idx->pin[b], m * src_row, cudaMemcpyHostToDevice, s);
             }
             if (e == cudaSuccess) {
-                rc = vq::prep_rows_launch(idx->stage[b], src_dtype, idx->d, dst + r0 * row, idx->dtype, idx->ld, (long long)m, idx->d, l2norm, s);
+                rc = to_storage(idx, idx->stage[b], src_dtype, dst + r0 * row, (long long)m, l2norm, 0, s);
                 if (rc == 0) e = cudaEventRecord(idx->ingest_ev[b], s);
             }
             if (e != cudaSuccess || rc) {
@@ -314,7 +336,7 @@ int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* ds
     const size_t row = (size_t)idx->ld * esize(idx->dtype);
     const uint8_t* src = (const uint8_t*)idx->data + start * row;
     if (is_device_ptr(dst)) {
-        int rc = vq::prep_rows_launch(src, idx->dtype, idx->ld, dst, dst_dtype, idx->d, (long long)n, idx->d, 0, s);
+        int rc = from_storage(idx, src, dst, dst_dtype, (long long)n, s);
         if (rc) return fail(VQ_ERR_CUDA, "vq_index_copy_rows: launch failed (%d)", rc);
         return VQ_OK;
     }
@@ -326,7 +348,7 @@ int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* ds
     CUDA_TRY(cudaMalloc(&stage, chunk * dst_row));
     for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
         const uint64_t m = (n - r0 < chunk) ? n - r0 : chunk;
-        int rc = vq::prep_rows_launch(src + r0 * row, idx->dtype, idx->ld, stage, dst_dtype, idx->d, (long long)m, idx->d, 0, s);
+        int rc = from_storage(idx, src + r0 * row, stage, dst_dtype, (long long)m, s);
         cudaError_t e = rc ? cudaErrorUnknown : cudaMemcpyAsync((uint8_t*)dst + r0 * dst_row, stage, m * dst_row, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) {
@@ -408,7 +430,7 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     } else {
         int variant = idx->variant;
         if (variant == VQ_VARIANT_AUTO) variant = (nq <= 128) ? VQ_VARIANT_TC_CG1 : VQ_VARIANT_TC_CG2;
-        if (variant == VQ_VARIANT_STREAM && nq > 32) variant = VQ_VARIANT_TC_CG1;
+        if (variant == VQ_VARIANT_STREAM && (nq > 32 || idx->dtype == VQ_F32X3)) variant = VQ_VARIANT_TC_CG1;
         if (variant == VQ_VARIANT_STREAM) {
             sp->kind = 2;
             vq::stream_plan(nq, n, idx->n_sms, &sp->st);
@@ -495,7 +517,7 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
         for (int p = 0; p < sp.n_passes && !rc; p++) {
             const bool last = p == sp.n_passes - 1;
             vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, 1, ub_score, ub_row};
-            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.tc[p], pass, lists, counts, progress, s);
+            rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->kd, idx->kdtype, k, sp.tc[p], pass, lists, counts, progress, s);
             // first pass: every row is a candidate; primed passes add ~ratio * k candidates per query
             const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : 4096;
             if (!rc)
@@ -517,7 +539,7 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
         }
     } else {
         if (ub_score) return -3;  // the streaming kernel has no banded mode
-        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->d, idx->dtype, k, sp.st,
+        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->kd, idx->kdtype, k, sp.st,
                                     lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
         if (!rc)
             rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, id_offset, nullptr, out_scores, out_ids,
@@ -544,7 +566,7 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     if (workspace_bytes < need) return fail(VQ_ERR_NOMEM, "vq_index_search: workspace %zu < %zu bytes", workspace_bytes, need);
     uint8_t* ws = (uint8_t*)workspace;
     void* qprep = ws + sp.off_q;
-    int rc = vq::prep_rows_launch(q, q_dtype, idx->d, qprep, idx->dtype, idx->ld, nq, idx->d, l2norm_q, s);
+    int rc = to_storage(idx, q, q_dtype, qprep, nq, l2norm_q, 1, s);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
     idx->launches += 1;
     // rows [nq, nq_pad) of the prepared query matrix are real zero rows, so the tensor-core path never

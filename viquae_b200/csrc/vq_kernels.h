@@ -6,6 +6,7 @@
 #define VQ_DTYPE_F32 0
 #define VQ_DTYPE_BF16 1
 #define VQ_DTYPE_F16 2
+#define VQ_DTYPE_F32X3 3
 
 namespace vq {
 
@@ -14,6 +15,14 @@ namespace vq {
 // columns d..ld_dst-1 are zero-filled.
 int prep_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
                      long long n, int d, int l2norm, cudaStream_t stream);
+// VQ_F32X3 storage: [n, 6*seg] bf16 per row, six segments of seg columns.  Corpus side: lo hi mid mid hi hi;
+// query side: hi lo mid hi mid hi (segment s of a query row times segment s of a corpus row are the six product terms,
+// smallest first).  split: src rows -> segments (optional L2 normalisation first, same arithmetic as prep_rows);
+// join: corpus-side segments -> hi + (mid + lo), exactly the fp32 value that was split.
+int split_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int seg, long long n, int d, int l2norm,
+                      int query_side, cudaStream_t stream);
+int join_rows_launch(const void* src, int seg, void* dst, int dst_dtype, long long ld_dst, long long n, int d, cudaStream_t stream);
+
 
 // ---- K3: tensor-core contraction + fused top-k (vq_tc.cu)
 struct TcPlan {

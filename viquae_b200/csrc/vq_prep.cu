@@ -72,6 +72,101 @@ static int prep_dispatch_dst(const void* src, long long ld_src, void* dst, int d
     return e == cudaSuccess ? 0 : -(int)e;
 }
 
+// fp32 value -> three bf16 terms with hi + mid + lo == v exactly (each remainder is exact in fp32)
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(mid);
+    lo = __float2bfloat16_rn(r2);
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const S* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst, int seg, long long n, int d, int l2norm,
+                  int query_side) {
+    const int lane = threadIdx.x & 31;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps_total) {
+        const S* s = src + row * ld_src;
+        __nv_bfloat16* o = dst + row * 6 * (long long)seg;
+        float div = 1.0f;
+        if (l2norm) {  // same arithmetic as prep_rows_kernel: the normalised fp32 values are those of an fp32 index
+            float acc = 0.0f;
+            for (int j = lane; j < d; j += 32) {
+                const float v = to_f32<S>(s[j]);
+                acc = fmaf(v, v, acc);
+            }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(VQ_FULL_MASK, acc, o2);
+            div = sqrtf(acc);
+        }
+        for (int j = lane; j < seg; j += 32) {
+            float v = 0.0f;
+            if (j < d) {
+                v = to_f32<S>(s[j]);
+                if (l2norm) v = v / div;
+            }
+            __nv_bfloat16 hi, mid, lo;
+            split3(v, hi, mid, lo);
+            if (query_side) {
+                o[j] = hi; o[seg + j] = lo; o[2 * seg + j] = mid; o[3 * seg + j] = hi; o[4 * seg + j] = mid; o[5 * seg + j] = hi;
+            } else {
+                o[j] = lo; o[seg + j] = hi; o[2 * seg + j] = mid; o[3 * seg + j] = mid; o[4 * seg + j] = hi; o[5 * seg + j] = hi;
+            }
+        }
+    }
+}
+
+template <typename D>
+__global__ void __launch_bounds__(256)
+join_rows_kernel(const __nv_bfloat16* __restrict__ src, int seg, D* __restrict__ dst, long long ld_dst, long long n, int d) {
+    const int lane = threadIdx.x & 31;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps_total) {
+        const __nv_bfloat16* s = src + row * 6 * (long long)seg;
+        D* o = dst + row * ld_dst;
+        for (int j = lane; j < d; j += 32) {
+            const float lo = __bfloat162float(s[j]), mid = __bfloat162float(s[2 * seg + j]), hi = __bfloat162float(s[5 * seg + j]);
+            const float v = hi + (mid + lo);
+            o[j] = from_f32<D>(v == 0.0f ? hi : v);  // a zero keeps its sign (hi is then +-0)
+        }
+    }
+}
+
+static unsigned row_blocks(long long n) {
+    long long blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    return (unsigned)blocks;
+}
+
+int split_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int seg, long long n, int d, int l2norm,
+                      int query_side, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    __nv_bfloat16* o = (__nv_bfloat16*)dst;
+    switch (src_dtype) {
+        case VQ_DTYPE_F32: split_rows_kernel<float><<<row_blocks(n), 256, 0, stream>>>((const float*)src, ld_src, o, seg, n, d, l2norm, query_side); break;
+        case VQ_DTYPE_BF16: split_rows_kernel<__nv_bfloat16><<<row_blocks(n), 256, 0, stream>>>((const __nv_bfloat16*)src, ld_src, o, seg, n, d, l2norm, query_side); break;
+        case VQ_DTYPE_F16: split_rows_kernel<__half><<<row_blocks(n), 256, 0, stream>>>((const __half*)src, ld_src, o, seg, n, d, l2norm, query_side); break;
+        default: return -2;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+int join_rows_launch(const void* src, int seg, void* dst, int dst_dtype, long long ld_dst, long long n, int d, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    const __nv_bfloat16* s = (const __nv_bfloat16*)src;
+    switch (dst_dtype) {
+        case VQ_DTYPE_F32: join_rows_kernel<float><<<row_blocks(n), 256, 0, stream>>>(s, seg, (float*)dst, ld_dst, n, d); break;
+        case VQ_DTYPE_BF16: join_rows_kernel<__nv_bfloat16><<<row_blocks(n), 256, 0, stream>>>(s, seg, (__nv_bfloat16*)dst, ld_dst, n, d); break;
+        case VQ_DTYPE_F16: join_rows_kernel<__half><<<row_blocks(n), 256, 0, stream>>>(s, seg, (__half*)dst, ld_dst, n, d); break;
+        default: return -2;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
 int prep_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
                      long long n, int d, int l2norm, cudaStream_t stream) {
     switch (src_dtype) {

@@ -48,7 +48,8 @@ except Exception:  # pragma: no cover - exercised only where `datasets` is absen
 METRIC_INNER_PRODUCT = 0  # faiss.METRIC_INNER_PRODUCT; `"metric_type": 0` in the shipped configs
 METRIC_L2 = 1
 _DTYPES = {"f32": _lib.F32, "fp32": _lib.F32, "float32": _lib.F32, "bf16": _lib.BF16, "bfloat16": _lib.BF16,
-           "f16": _lib.F16, "fp16": _lib.F16, "float16": _lib.F16}
+           "f16": _lib.F16, "fp16": _lib.F16, "float16": _lib.F16, "f32x3": _lib.F32X3}
+_WIDE = (_lib.F32, _lib.F32X3)  # storage types that hold full fp32 values
 _VARIANTS = {None: _lib.VARIANT_AUTO, "auto": _lib.VARIANT_AUTO, "tc_cg1": _lib.VARIANT_TC_CG1,
              "tc_cg2": _lib.VARIANT_TC_CG2, "stream": _lib.VARIANT_STREAM}
 
@@ -93,7 +94,8 @@ class B200FlatIndex(BaseIndex):
     """Exact inner-product top-k index living in the HBM of one B200.
 
     Parameters mirror ``FaissIndex(device, string_factory, metric_type)`` plus the storage ``dtype``
-    ("bf16" default: tensor-core path; "f16"; "f32": exact fixed-order mode).
+    ("bf16" default: tensor-core path; "f16"; "f32": exact fixed-order mode; "f32x3": fp32 values split into three
+    bf16 terms and contracted on the tensor cores with fp32 accumulation — fp32-faithful scores, 12 bytes/element).
     """
 
     def __init__(self, d: Optional[int] = None, dtype: str = "bf16", device: int = 0, string_factory: Optional[str] = "Flat",
@@ -304,6 +306,8 @@ class B200FlatIndex(BaseIndex):
     def reconstruct_n(self, start: int = 0, n: Optional[int] = None, dtype: str = "f32") -> np.ndarray:
         n = self.ntotal - start if n is None else n
         code = _DTYPES[dtype]
+        if code == _lib.F32X3:
+            raise ValueError("reconstruct_n: 'f32x3' is a storage layout, ask for 'f32', 'bf16' or 'f16' rows")
         out = np.empty((n, self.d), dtype=np.float32 if code == _lib.F32 else np.uint16)
         if n:
             _lib.check(_lib.load().vq_index_copy_rows(self._h, start, n, out.ctypes.data, code, None))
@@ -315,7 +319,7 @@ class B200FlatIndex(BaseIndex):
         bf16/f16).  Rows are stored after ingest-time normalisation, so loading never re-normalises."""
         file = os.fspath(file)
         code = _DTYPES[self.dtype]
-        rows = self.reconstruct_n(0, None, "f32" if code == _lib.F32 else self.dtype)
+        rows = self.reconstruct_n(0, None, "f32" if code in _WIDE else self.dtype)
         np.save(file + ".npy", rows, allow_pickle=False)
         with open(file, "wt") as f:
             json.dump({"format": "viquae_b200.flat_ip.v1", "d": self.d, "ntotal": self.ntotal, "dtype": self.dtype,
@@ -341,6 +345,8 @@ class B200FlatIndex(BaseIndex):
         idx = cls(d=hdr["d"], dtype=hdr["dtype"], device=device, string_factory=hdr["string_factory"],
                   capacity=hdr["ntotal"], variant=variant, id_offset=hdr.get("id_offset", 0))
         code = _DTYPES[hdr["dtype"]]
+        if code == _lib.F32X3:
+            code = _lib.F32  # saved as the exact fp32 values, split again on ingest
         if hdr["ntotal"]:
             rows = np.ascontiguousarray(rows)
             _lib.check(_lib.load().vq_index_add(idx._h, rows.ctypes.data, rows.shape[0], code, 0, None))
