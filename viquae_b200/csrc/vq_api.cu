@@ -302,6 +302,9 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
         const size_t src_row = (size_t)idx->d * esize(src_dtype);
         uint64_t chunk = VQ_INGEST_CHUNK / src_row;
         if (chunk < 1) chunk = 1;
+        if (chunk > n) chunk = n;  // small adds keep small buffers (they grow with the first large one)
+        if (idx->ingest_bytes >= src_row && chunk * src_row > idx->ingest_bytes && idx->ingest_bytes * 8 >= chunk * src_row)
+            chunk = idx->ingest_bytes / src_row;  // buffers within 8x of the wish: reuse them rather than reallocate pinned memory
         cudaError_t e = ingest_reserve(idx, chunk * src_row);
         if (e != cudaSuccess) return fail(VQ_ERR_NOMEM, "vq_index_add: ingest buffers: %s", cudaGetErrorString(e));
         uint64_t c = 0;
@@ -440,11 +443,12 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
             sp->kind = 1;
             const int cg = variant == VQ_VARIANT_TC_CG2 ? 2 : 1;
             // Threshold priming.  A query's k-th best score over ANY subset of the corpus is a lower bound of its
-            // final k-th best score, so the corpus is searched in passes of geometrically growing size (x16): the
-            // first pass is one tile per work item (nothing to prune yet), every later pass starts from the k-th
-            // score of everything before it and therefore rejects almost every 32-score block with a single
-            // compare; it appends only ~8k candidates per query.  Rows of later passes have higher ids, so a
-            // score equal to the threshold loses the tie and the strict compare stays exact.
+            // final k-th best score, so the corpus is searched in passes of geometrically growing size (x ratio), each
+            // a strided sample of the whole corpus (pass_schedule above): the first pass has about one tile per work
+            // item (nothing to prune yet), every later pass starts just below the k-th score of everything before it
+            // and rejects almost every 32-score block with a single compare; it appends only ~ratio * k candidates
+            // per query.  The handed-down threshold is the next float below the k-th score (merge_lists_kernel), so
+            // an equal score with a lower id still gets in and the result stays exact.
             const int n_tiles = (int)((n + 255) / 256);
             const int m_tiles = (nq + 128 * cg - 1) / (128 * cg);
             static int env_first = -1, env_ratio = -1;  // experiment knobs: VQ_FIRST_TILES, VQ_PASS_RATIO
