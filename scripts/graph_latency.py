@@ -7,7 +7,9 @@ from viquae_b200.index import B200FlatIndex
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, nargs="+", default=[1_500_000, 12_000_000])
-ap.add_argument("--calls", type=int, default=300)
+ap.add_argument("--calls", type=int, default=1000)
+ap.add_argument("--warmup", type=int, default=50)
+ap.add_argument("--nq", type=int, nargs="+", default=[1, 2, 4, 8, 16, 32])
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 for rows in args.rows:
@@ -15,7 +17,7 @@ for rows in args.rows:
     for c0 in range(0, rows, 1_000_000):
         g = torch.Generator(device=dev); g.manual_seed(20240117 + c0 // 1_000_000)
         idx.add(torch.randn((min(1_000_000, rows - c0), 768), generator=g, device=dev).to(torch.bfloat16))
-    for nq in (1, 8, 32):
+    for nq in args.nq:
         g = torch.Generator(device=dev); g.manual_seed(7)
         q = torch.randn((nq, 768), generator=g, device=dev)
         out = (torch.empty((nq, 100), device=dev), torch.empty((nq, 100), dtype=torch.int64, device=dev))
@@ -23,7 +25,7 @@ for rows in args.rows:
         cap.queries.copy_(q)
 
         def timed(fn):
-            for _ in range(20):
+            for _ in range(args.warmup):
                 fn()
             torch.cuda.synchronize()
             lat = []
@@ -39,6 +41,7 @@ for rows in args.rows:
         ideal = rows * 768 * 2 / 6540.5e9 * 1e6
         print(json.dumps({"rows": rows, "nq": nq, "plain_p50_us": round(p_plain[0], 1), "plain_p99_us": round(p_plain[1], 1),
                           "graph_p50_us": round(p_graph[0], 1), "graph_p99_us": round(p_graph[1], 1),
+                          "graph_queries_per_s": round(nq / p_graph[0] * 1e6), "calls": args.calls, "warmup": args.warmup,
                           "hbm_ideal_us": round(ideal, 1), "identical": same,
                           "ids_sum": int(cap.ids.sum()), "scores_sum": float(cap.scores.double().sum())}), flush=True)
     idx.close()
