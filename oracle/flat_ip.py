@@ -56,6 +56,28 @@ def fp16_round(x: np.ndarray) -> np.ndarray:
     return np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float32)
 
 
+def split3_bf16(x: np.ndarray):
+    """The engine's VQ_F32X3 storage (viquae_b200/csrc/vq_prep.cu: split3): an fp32 value as three bf16 terms
+    hi + mid + lo with every remainder exact in fp32, so the three terms sum to the value.  Not a reference
+    function — FAISS holds plain fp32 (datasets/search.py:276-288); this restates OUR layout so its arithmetic can
+    be checked on the CPU."""
+    x = np.asarray(x, np.float32)
+    hi = bf16_round(x)
+    r1 = (x - hi).astype(np.float32)
+    mid = bf16_round(r1)
+    r2 = (r1 - mid).astype(np.float32)
+    lo = bf16_round(r2)
+    return hi, mid, lo
+
+
+def f32x3_scores(Q, X) -> np.ndarray:
+    """Scores of the six-term split contraction (hi*lo + lo*hi + mid*mid + hi*mid + mid*hi + hi*hi), every product
+    exact and the sums in float64: isolates the error of the three dropped terms from accumulation rounding."""
+    qh, qm, ql = (t.astype(np.float64) for t in split3_bf16(Q))
+    xh, xm, xl = (t.astype(np.float64) for t in split3_bf16(X))
+    return qh @ xl.T + ql @ xh.T + qm @ xm.T + qh @ xm.T + qm @ xh.T + qh @ xh.T
+
+
 def _select_topk(scores: np.ndarray, ids: np.ndarray, k: int):
     """Exact top-k of one row: descending score, ties -> lower id; unselectable values dropped.
 

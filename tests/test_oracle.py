@@ -116,3 +116,24 @@ def test_wsum_union_and_order():
     assert list(fused["q"].items()) == [("2", 0.75), ("1", 0.5), ("3", 0.125)]
     z = fuse_oracle.zmuv_norm({"q": {"1": 2.0}})
     assert z["q"]["1"] == 0.0  # single result: std 0 -> denominator 1e-9
+
+
+def test_f32x3_split_is_exact_and_six_terms_are_fp32_faithful():
+    """The VQ_F32X3 layout on the CPU: three bf16 terms reproduce every fp32 value exactly, and the six product
+    terms the tensor cores accumulate miss the exact inner product by less than 2^-23 of sum |q_j x_j|."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.standard_normal(200_000).astype(np.float32),
+                        (rng.standard_normal(50_000) * 1e-20).astype(np.float32), (rng.standard_normal(50_000) * 1e20).astype(np.float32),
+                        np.array([0.0, -0.0, 1.0, -1.0, 3.3895314e38, 1.1754944e-38, 65504.0, 1 + 2.0 ** -23], np.float32)])
+    hi, mid, lo = flat_ip.split3_bf16(x)
+    back = (hi + (mid + lo)).astype(np.float32)
+    assert np.array_equal(back, x)  # value-exact (a zero's sign is restored from hi in join_rows_kernel)
+    for t in (hi, mid, lo):
+        assert np.array_equal(flat_ip.bf16_round(t), t)  # every term is a bf16 value
+    Q = rng.standard_normal((16, 768)).astype(np.float32)
+    X = rng.standard_normal((4000, 768)).astype(np.float32)
+    exact = Q.astype(np.float64) @ X.astype(np.float64).T
+    got = flat_ip.f32x3_scores(Q, X)
+    bound = (np.abs(Q).astype(np.float64) @ np.abs(X).astype(np.float64).T) * 2.0 ** -23
+    assert np.all(np.abs(got - exact) <= bound)
+    assert float(np.max(np.abs(got - exact) / np.maximum(np.abs(exact), np.sqrt(768)))) < 2e-7
