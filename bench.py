@@ -1,21 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the exact inner-product top-k engine (BASELINE.json metric).
+"""bench.py — benchmarks of the exact inner-product top-k engine (BASELINE.json metric and configs).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nq 1250] [--rows 12000000]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4|5]
+                    [--nq ..] [--rows ..] [--dtype ..]
 
-A "step" = one pass of the hot path over one batch of synthetic queries: exact IP top-100 of
-`nq` (default 1,250) 768-d queries against the 12M x 768 bf16 synthetic passage corpus
-(BASELINE.json configs[1]).  With N GPUs the corpus is row-sharded over the ranks
-(viquae_b200.sharded), every step includes the all-gather of the per-rank candidates and the
-k-way merge.  Rank 0 prints ONE JSON line (see README / DESIGN.md for the keys).
+A "step" = one pass of the hot path over one batch of synthetic queries.  `--config` picks the BASELINE.json
+configuration (1-based index into `configs`); every one prints the same one-line JSON contract:
 
-`--impl reference` times the reference's CPU path instead: FAISS is not installable offline, so
-it is the FAISS-equivalent CPU port in oracle/flat_ip.py (blocked sgemm on all host cores +
-k-selection) on a bounded sample of the same synthetic inputs.
+  2 (default, the headline)  exact IP top-100 of 1,250 768-d queries against the 12M x 768 bf16 synthetic passage
+                             corpus, row-sharded over the N ranks; every step includes the exchange and the merge
+  1  validation batch        1,250 queries x 1.5M rows, fp32 inputs: f32x3 (fp32-faithful tensor-core mode) as the
+                             line's value, the bit-exact SIMT mode and bf16 in `modes`
+  3  multimodal fusion       text + image + face indexes, article->passage expansion, gzmuv + defmin + wsum
+  4  hard-negative mining    65,536 queries x 12M rows, bf16 as the line's value, fp16 and an fp32-exact slice in `modes`
+  5  latency regime          batch 1..32 over 12M rows, 1000 calls after 50 warm-ups each, CUDA-graph replay, p50/p99
+
+After the timed loops rank 0 adds `result_sha` (a digest of the step's ids and scores: identical for every N,
+the kernels are deterministic and ties break by id) and `parity_check` (32 queries: the returned rows' inner
+products recomputed in float64 from regenerated corpus chunks, and no sampled row beats the k-th score).
+
+`--impl reference` times the reference's CPU path instead: FAISS is not installable offline, so it is the
+FAISS-equivalent CPU port in oracle/flat_ip.py (blocked sgemm on all host cores + k-selection).  A step there is
+one reference-sized `search_batch` call (256 queries, meerqat's map batch size) over the FULL corpus when the
+host has the RAM for it (no extrapolation), else all queries over a row sample, scaled and labelled.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,24 +41,41 @@ sys.path.insert(0, ROOT)
 CHUNK_ROWS = 1_000_000
 CORPUS_SEED = 20240117  # chunk c uses seed CORPUS_SEED + c: identical corpus for every GPU count
 QUERY_SEED = 7
+METRIC = "queries/s exact top-100 over 12Mx768 passages"
+REF_CALL_QUERIES = 256  # queries per search_batch call in every shipped config (map_kwargs.batch_size)
+
+CONFIG_DEFAULTS = {
+    1: dict(rows=1_500_000, nq=1250, dtype="f32x3", steps=20, warmup=3),
+    2: dict(rows=12_000_000, nq=1250, dtype="bf16", steps=20, warmup=3),
+    3: dict(rows=12_000_000, nq=1250, dtype="bf16", steps=10, warmup=3),
+    4: dict(rows=12_000_000, nq=65536, dtype="bf16", steps=3, warmup=3),
+    5: dict(rows=12_000_000, nq=32, dtype="bf16", steps=1000, warmup=50),
+}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nq", type=int, default=1250)
-    ap.add_argument("--rows", type=int, default=12_000_000)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--nq", type=int, default=None)
+    ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=100)
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32", "f32x3"])
+    ap.add_argument("--dtype", default=None, choices=[None, "bf16", "f16", "f32", "f32x3"])
     ap.add_argument("--variant", default=None, choices=[None, "auto", "tc_cg1", "tc_cg2", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--latency-calls", type=int, default=0, help="also time this many single calls end to end (p50/p99, BASELINE config 5)")
-    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="corpus rows of the CPU sample (default: 1.5M inline, 3M for --impl reference)")
-    return ap.parse_args()
+    ap.add_argument("--no-modes", action="store_true", help="configs 1 and 4: skip the secondary storage modes")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--latency-calls", type=int, default=0, help="config 2: also time this many single host-buffer calls (p50/p99)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="force the CPU arm onto a row sample of this size (scaled)")
+    args = ap.parse_args()
+    for key, val in CONFIG_DEFAULTS[args.config].items():
+        if getattr(args, key) is None:
+            setattr(args, key, val)
+    return args
 
 
 # ----------------------------------------------------------------------------- synthetic inputs
@@ -62,6 +91,11 @@ def gen_queries(nq: int, dim: int, device, dtype):
     g = torch.Generator(device=device)
     g.manual_seed(QUERY_SEED)
     return torch.randn((nq, dim), generator=g, device=device, dtype=torch.float32).to(dtype)
+
+
+def torch_dtype(name):
+    import torch
+    return {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "f32x3": torch.float32}[name]
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -94,49 +128,94 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.1] or [r for (_, r) in self.rows[-3:]]
-        sm, mx, reasons = [], None, set()
+        sm, mx, power, reasons = [], None, [], set()
         for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
+                power.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
 
 
 # ----------------------------------------------------------------------------- CPU port (reference arm / cpu_baseline)
-def cpu_port_sample(args, device, sample_rows: int, repeats: int = 1, warmup: int = 0):
-    """Times the FAISS-equivalent CPU port on all queries x the first `sample_rows` corpus rows
-    (fp32 upcast of the SAME synthetic bf16 values) and scales the time linearly to the full corpus."""
-    import numpy as np
-    import torch
-    from oracle import flat_ip
+def host_ram_available() -> int:
+    avail = 0
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            txt = open(path).read().strip()
+            if txt.isdigit():
+                limit = int(txt)
+                used = 0
+                for up in ("/sys/fs/cgroup/memory.current", "/sys/fs/cgroup/memory/memory.usage_in_bytes"):
+                    try:
+                        used = int(open(up).read().strip())
+                        break
+                    except Exception:
+                        pass
+                avail = min(avail, limit - used) if avail else limit - used
+        except Exception:
+            pass
+    return avail
 
-    dt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "f32x3": torch.float32}[args.dtype]
-    sample_rows = min(sample_rows, args.rows)
-    parts, c, left = [], 0, sample_rows
-    while left > 0:
-        n = min(CHUNK_ROWS, args.rows - c * CHUNK_ROWS)
-        x = gen_chunk(c, n, args.dim, device, dt)[:left]
-        parts.append(x.float().cpu())
-        left -= x.shape[0]
-        c += 1
-    X = torch.cat(parts).contiguous()
-    Q = gen_queries(args.nq, args.dim, device, dt).float().cpu().numpy()
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    times = []
-    for it in range(warmup + repeats):
+
+class CpuPort:
+    """The FAISS-equivalent CPU port on the SAME synthetic values (fp32 upcast of what the GPU index stores).
+    Builds the host copy once; `step()` is one timed pass."""
+
+    def __init__(self, args, device, force_rows: int = 0):
+        import torch
+
+        dt = torch_dtype(args.dtype)
+        full_bytes = args.rows * args.dim * 4
+        want_full = not force_rows and host_ram_available() > full_bytes * 1.15 + (6 << 30)
+        self.rows_total = args.rows
+        self.sample_rows = args.rows if want_full else min(args.rows, force_rows or 3_000_000)
+        self.extrapolated = self.sample_rows < args.rows
+        # full corpus: one reference-sized search_batch call per step; row sample: all queries, time scaled
+        self.nq_step = min(args.nq, REF_CALL_QUERIES) if not self.extrapolated else args.nq
+        self.scale = args.rows / float(self.sample_rows)
+        self.X = torch.empty((self.sample_rows, args.dim), dtype=torch.float32)
+        c, done = 0, 0
+        while done < self.sample_rows:
+            n = min(CHUNK_ROWS, args.rows - c * CHUNK_ROWS)
+            x = gen_chunk(c, n, args.dim, device, dt)[: self.sample_rows - done]
+            self.X[done:done + x.shape[0]].copy_(x.float())
+            done += x.shape[0]
+            c += 1
+        self.Q = gen_queries(args.nq, args.dim, device, dt).float().cpu().numpy()[: self.nq_step]
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.k = args.k
+        self.dtype = args.dtype
+
+    def step(self) -> float:
+        from oracle import flat_ip
+
         t0 = time.perf_counter()
-        flat_ip.flat_ip_search_fast(Q, X, args.k)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    scale = args.rows / float(sample_rows)
-    return times, scale, cores, sample_rows
+        flat_ip.flat_ip_search_fast(self.Q, self.X, self.k)
+        return time.perf_counter() - t0
+
+    def queries_per_s(self, seconds: float) -> float:
+        return self.nq_step / (seconds * self.scale)
+
+    def describe(self, n_timed: int) -> str:
+        if self.extrapolated:
+            return (f"all {self.nq_step} queries x first {self.sample_rows} of {self.rows_total} rows (fp32 upcast of the same synthetic "
+                    f"{self.dtype} values), {n_timed} timed passes, time scaled x{self.scale:.2f} to the full corpus")
+        return (f"one {self.nq_step}-query search_batch call (the reference's call size) x all {self.rows_total} rows (fp32 upcast of the "
+                f"same synthetic {self.dtype} values), {n_timed} timed calls, no extrapolation")
 
 
 def run_reference(args):
@@ -145,19 +224,19 @@ def run_reference(args):
     if rank != 0:
         return
     device = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
-    times, scale, cores, sample_rows = cpu_port_sample(args, device, args.cpu_sample_rows or 3_000_000, repeats=max(1, args.steps),
-                                                       warmup=max(0, min(args.warmup, 1)))
-    step_s = sum(times) / len(times) * scale
-    value = args.nq / step_s
-    sample = (f"all {args.nq} queries x first {sample_rows} of {args.rows} rows (fp32 upcast of the same synthetic "
-              f"{args.dtype} values), {len(times)} timed passes, time scaled x{scale:.2f} to the full corpus")
+    port = CpuPort(args, device, force_rows=args.cpu_sample_rows)
+    for _ in range(args.warmup):
+        port.step()
+    times = [port.step() for _ in range(max(1, args.steps))]
+    step_s = sum(times) / len(times)
+    value = port.queries_per_s(step_s)
     line = {
-        "impl": "reference", "metric": "queries/s exact top-100 over 12Mx768 passages", "value": value, "unit": "queries/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
-                         "sample_ms": sum(times) / len(times) * 1e3,
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": port.cores, "kind": "port", "sample": port.describe(len(times)),
+                         "sample_ms": step_s * 1e3, "extrapolated": port.extrapolated,
                          "note": "FAISS-equivalent CPU port (oracle/flat_ip.py: torch/MKL sgemm blocks + top-k merge); faiss itself is not installable offline"},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -166,202 +245,550 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    names = {1: "configs[0] validation batch", 2: "configs[1] headline", 3: "configs[2] multimodal fusion",
+             4: "configs[3] hard-negative mining batch", 5: "configs[4] latency regime"}
     return {"workload": f"{args.rows}x{args.dim} {args.dtype} synthetic N(0,1) passage corpus, {args.nq} queries/step, exact IP top-{args.k}",
-            "rows": args.rows, "dim": args.dim, "nq": args.nq, "k": args.k, "sharding": f"rows/{world}",
+            "baseline_config": names[args.config], "rows": args.rows, "dim": args.dim, "nq": args.nq, "k": args.k, "sharding": f"rows/{world}",
             "l2_policy": "inputs_larger_than_L2 (corpus shard >= 2.3 GB vs 126 MB L2)"}
 
 
-# ----------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from viquae_b200 import _lib
-    from viquae_b200.index import B200FlatIndex
-    from viquae_b200.sharded import ShardedFlatIndex, shard_range
+# ----------------------------------------------------------------------------- distributed context
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU port)")
-    torch.cuda.set_device(local_rank)
-    device = torch.device(f"cuda:{local_rank}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    dt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32, "f32x3": torch.float32}[args.dtype]
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU port)")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device(f"cuda:{self.local_rank}")
+        self.dist = dist
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
 
-    # ---- build the local shard on the device (nothing is shipped to the box)
-    r0, r1 = shard_range(args.rows, rank, world)
-    index = B200FlatIndex(d=args.dim, dtype=args.dtype, device=local_rank, capacity=r1 - r0, variant=args.variant, id_offset=r0)
-    c = r0 // CHUNK_ROWS
-    while c * CHUNK_ROWS < r1:
-        c0, c1 = c * CHUNK_ROWS, min(args.rows, (c + 1) * CHUNK_ROWS)
-        x = gen_chunk(c, c1 - c0, args.dim, device, dt)
-        lo, hi = max(r0, c0) - c0, min(r1, c1) - c0
-        index.add(x[lo:hi])
-        del x
-        c += 1
-    assert index.ntotal == r1 - r0
-    sharded = ShardedFlatIndex(index, rank=rank, world_size=world) if world > 1 else None
-    q_dev = gen_queries(args.nq, args.dim, device, dt)
-    q_host = q_dev.float().cpu().pin_memory()
-    k = args.k
-    lib = _lib.load()
-
-    def step_device():
-        if sharded is not None:
-            return sharded.search_tensors(q_dev, k)
-        return index.search_tensors(q_dev, k)
-
-    out_s_host = torch.empty((args.nq, k), dtype=torch.float32).pin_memory()
-    out_i_host = torch.empty((args.nq, k), dtype=torch.int64).pin_memory()
-
-    def step_e2e():
-        # the call a user of the reference makes: host float32 queries in, host (scores, ids) out
-        if sharded is None:
-            _lib.check(lib.vq_index_search_host(index._h, q_host.data_ptr(), args.nq, 0, k, out_s_host.data_ptr(), out_i_host.data_ptr()))
-        else:
-            q = q_host.to(device, non_blocking=True)
-            s, i = sharded.search_tensors(q, k)
-            out_s_host.copy_(s, non_blocking=True)
-            out_i_host.copy_(i, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def max_over_ranks(self, ms: float) -> float:
+        import torch
+        t = torch.tensor([ms], device=self.device, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup):
+        """W untimed calls, then EXACTLY `steps` calls between two CUDA events, barrier + synchronize on both sides, max over ranks."""
+        import torch
         for _ in range(warmup):
             fn()
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
+        self.barrier()
         t1 = time.time()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), t0, t1
+        return self.max_over_ranks(e0.elapsed_time(e1)), t0, t1
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def build_shard(ctx, rows, dim, dtype, variant=None):
+    from viquae_b200.index import B200FlatIndex
+    from viquae_b200.sharded import ShardedFlatIndex, shard_range
+
+    dt = torch_dtype(dtype)
+    r0, r1 = shard_range(rows, ctx.rank, ctx.world)
+    index = B200FlatIndex(d=dim, dtype=dtype, device=ctx.local_rank, capacity=r1 - r0, variant=variant, id_offset=r0)
+    c = r0 // CHUNK_ROWS
+    while c * CHUNK_ROWS < r1:
+        c0, c1 = c * CHUNK_ROWS, min(rows, (c + 1) * CHUNK_ROWS)
+        x = gen_chunk(c, c1 - c0, dim, ctx.device, dt)
+        lo, hi = max(r0, c0) - c0, min(r1, c1) - c0
+        index.add(x[lo:hi])
+        del x
+        c += 1
+    assert index.ntotal == r1 - r0
+    sharded = ShardedFlatIndex(index, rank=ctx.rank, world_size=ctx.world) if ctx.world > 1 else None
+    return index, sharded, (r0, r1)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {}, "fallback"
+
+
+# ----------------------------------------------------------------------------- result digest + parity spot check
+def result_digest(s, i):
+    ids = i.cpu().numpy()
+    sc = s.cpu().numpy()
+    return {"result_sha": hashlib.sha256(ids.tobytes() + sc.tobytes()).hexdigest()[:16],
+            "ids_sha": hashlib.sha256(ids.tobytes()).hexdigest()[:16]}
+
+
+def parity_check(args, ctx, s, i, q_dev, n_queries=32, sample_per_chunk=16384):
+    """Rank 0, after the timed loops.  For `n_queries` evenly spaced queries: (a) the score of every returned row is
+    recomputed in float64 from the regenerated corpus chunk (the same seeded values the shards were built from);
+    (b) per chunk, `sample_per_chunk` random rows are scored in float64 and none that is missing from the result may
+    beat the query's k-th score; (c) rows are descending, ids valid and unique.  A checker, not the product path:
+    torch float64 arithmetic on the device."""
+    import torch
+
+    dt = torch_dtype(args.dtype)
+    tol = 2e-3 if args.dtype in ("bf16", "f16") else 1e-5  # north_star tolerances (relative, on the same quantised inputs)
+    nq = s.shape[0]
+    sel = torch.unique(torch.linspace(0, nq - 1, min(n_queries, nq), device=s.device).round().long())
+    qs = q_dev[sel].double()
+    ids, sc = i[sel], s[sel].double()
+    k = ids.shape[1]
+    recomputed = torch.full_like(sc, float("nan"))
+    kth = sc[:, -1]
+    slack = tol * kth.abs()
+    g = torch.Generator(device=s.device)
+    g.manual_seed(99)
+    violations, sampled = 0, 0
+    n_chunks = (args.rows + CHUNK_ROWS - 1) // CHUNK_ROWS
+    for c in range(n_chunks):
+        c0, c1 = c * CHUNK_ROWS, min(args.rows, (c + 1) * CHUNK_ROWS)
+        x = gen_chunk(c, c1 - c0, args.dim, s.device, dt)
+        m = (ids >= c0) & (ids < c1)
+        if bool(m.any()):
+            qi, kj = m.nonzero(as_tuple=True)
+            recomputed[qi, kj] = (x[ids[qi, kj] - c0].double() * qs[qi]).sum(1)
+        samp = torch.randint(0, c1 - c0, (min(sample_per_chunk, c1 - c0),), generator=g, device=s.device)
+        sv = qs @ x[samp].double().T                                 # [sel, samples]
+        beats = sv > (kth + slack)[:, None]
+        if bool(beats.any()):
+            qi, sj = beats.nonzero(as_tuple=True)
+            present = (ids[qi] == (samp[sj] + c0)[:, None]).any(1)
+            violations += int((~present).sum().item())
+        sampled += samp.numel()
+        del x
+    rel = ((recomputed - sc).abs() / sc.abs().clamp_min(1e-30))
+    missing = int(torch.isnan(recomputed).sum().item())
+    max_rel = float(torch.nan_to_num(rel, nan=0.0).max().item())
+    descending = bool((sc[:, 1:] <= sc[:, :-1]).all().item())
+    unique = all(len(set(row.tolist())) == k for row in ids.cpu())
+    ok = missing == 0 and max_rel <= tol and violations == 0 and descending and unique
+    return {"ok": bool(ok), "queries_checked": int(sel.numel()), "max_rel_err": max_rel, "tolerance": tol,
+            "rows_sampled_per_query": sampled, "unreturned_rows_beating_kth": violations, "ids_unresolved": missing,
+            "descending": descending, "ids_unique": unique,
+            "how": "returned rows' scores recomputed in float64 from regenerated corpus chunks; random rows per chunk must not beat the k-th score"}
+
+
+# ----------------------------------------------------------------------------- configs 1, 2, 4: search throughput
+def measure_search(args, ctx, dtype, nq, rows, steps, warmup, with_e2e=True, variant=None):
+    """Builds the (sharded) index in `dtype`, times `steps` device-resident steps and `steps` end-to-end steps.
+    Returns a dict of raw measurements (+ the live objects for the digest)."""
+    import torch
+    from viquae_b200 import _lib
+
+    lib = _lib.load()
+    k = args.k
+    index, sharded, (r0, r1) = build_shard(ctx, rows, args.dim, dtype, variant)
+    dt = torch_dtype(dtype)
+    q_dev = gen_queries(nq, args.dim, ctx.device, dt)
+    q_host = q_dev.float().cpu().pin_memory()
+
+    def step_device():
+        if sharded is not None:
+            return sharded.search_tensors(q_dev, k)
+        return index.search_tensors(q_dev, k)
+
+    out_s_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        # the call a user of the reference makes: host float32 queries in, host (scores, ids) out
+        if sharded is None:
+            _lib.check(lib.vq_index_search_host(index._h, q_host.data_ptr(), nq, 0, k, out_s_host.data_ptr(), out_i_host.data_ptr()))
+        else:
+            # every rank holds the host batch (one process per GPU runs the same map); rank r uploads its slice,
+            # NVLink all-gather, search + exchange + merge, rank 0 reads the result back
+            sharded.search_host(q_host, k, out=(out_s_host, out_i_host), result_ranks=0)
+            torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(ctx.local_rank) if ctx.rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    # ---- device-resident throughput (+ CUDA events around the dominant kernel, recorded by the engine)
     _lib.check(lib.vq_index_set_timing(index._h, 0))
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     _lib.check(lib.vq_index_set_timing(index._h, 1))
     launches0 = int(lib.vq_index_launch_count(index._h))
-    total_ms, t0, t1 = timed(step_device, args.steps, 0)
-    launches_timed = int(lib.vq_index_launch_count(index._h)) - launches0 + (args.steps if world > 1 else 0)
-    tot = _lib.c_double()
-    nl = _lib.c_int()
+    total_ms, t0, t1 = ctx.timed(step_device, steps, 0)
+    launches = int(lib.vq_index_launch_count(index._h)) - launches0 + (steps if ctx.world > 1 else 0)  # + the cross-shard merge kernel
+    tot, nl = _lib.c_double(), _lib.c_int()
     _lib.check(lib.vq_index_read_timing(index._h, _lib.ctypes.byref(tot), _lib.ctypes.byref(nl)))
     _lib.check(lib.vq_index_set_timing(index._h, 0))
     clocks = sampler.stop(t0, t1) if sampler else None
-    # ---- end to end through the host-buffer API
-    e2e_ms, _, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_ms = None
+    if with_e2e:
+        e2e_ms, _, _ = ctx.timed(step_e2e, steps, warmup)
+    s, i = step_device()
+    torch.cuda.synchronize()
+    return {"index": index, "sharded": sharded, "q_dev": q_dev, "scores": s, "ids": i, "ms_per_step": total_ms / steps,
+            "e2e_ms_per_step": None if e2e_ms is None else e2e_ms / steps, "kernel_ms": tot.value / max(1, nl.value), "kernel_launches_timed": nl.value,
+            "launches": launches, "clocks": clocks, "local_rows": r1 - r0, "step_e2e": step_e2e, "h2d": nq * args.dim * 4,
+            "d2h": nq * k * 12}
 
+
+def roofline(args, dtype, nq, local_rows, kern_ms, world, rows):
+    peaks, peaks_src = load_peaks()
+    k = args.k
+    terms = 6 if dtype == "f32x3" else 1   # f32x3: six bf16 product terms per fp32 product, 12 stored bytes per element
+    flops = 2.0 * nq * local_rows * args.dim * terms
+    bytes_ = local_rows * args.dim * {"f32": 4, "f32x3": 12}.get(dtype, 2) + nq * args.dim * 2 * terms + nq * k * 12
+    if dtype == "f32":
+        # exact mode is SIMT FFMA-bound: 148 SMs x 128 FMA/clk x 2 flop at the max SM clock (no measured peak for it)
+        peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        roof = {"bound": "fp32-ffma", "achieved": flops / (kern_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s"}
+    elif nq * terms > 211:
+        roof = {"bound": "tensor", "achieved": flops / (kern_ms * 1e-3) / 1e12, "peak": float(peaks.get("bf16_tflops", 1590.0)), "unit": "TFLOP/s"}
+        if "bf16_tflops_sustained" in peaks:
+            roof["frac_of_sustained_peak"] = roof["achieved"] / float(peaks["bf16_tflops_sustained"])
+        if terms > 1:
+            roof["note"] = "bf16 tensor flops issued (6 product terms per fp32 product); fp32-equivalent rate = achieved / 6"
+    else:
+        roof = {"bound": "hbm", "achieved": bytes_ / (kern_ms * 1e-3) / 1e9, "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["peak_source"] = (f"{peaks_src} (MEASURED_PEAKS.json burst figure: kernel timed alone)" if peaks_src == "measured"
+                           else "fallback (B200_PROFILING.md)")
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch(es), from the committed
+    # `ncu --set full` capture of this same workload (profiles/traffic.json); null for other workloads
+    roof["traffic"] = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)
+        key = f"nq{nq}_rows{rows}_d{args.dim}_{dtype}_gpus{world}"
+        if key in tr:
+            roof["traffic"] = tr[key]["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr[key]["source"]
+    except Exception:
+        pass
+    roof["kernel"] = {"f32": "f32_topk_kernel"}.get(dtype, "tc_topk_kernel")
+    roof["timed_region"] = "all contraction passes of a step (threshold-priming passes + main pass) and their merge kernels; excludes only the query cast"
+    roof["kernel_ms"] = kern_ms
+    roof["algorithmic"] = {"flops_per_launch": flops, "bytes_per_launch": bytes_}
+    return roof
+
+
+def run_search_config(args, ctx):
+    import torch
+
+    m = measure_search(args, ctx, args.dtype, args.nq, args.rows, args.steps, args.warmup, variant=args.variant)
     latency = None
     if args.latency_calls > 0:
-        # per-call latency through the host-buffer API (what interact/system.py's one-question loop would see)
         lat = []
         for _ in range(50):
-            step_e2e()
+            m["step_e2e"]()
         for _ in range(args.latency_calls):
-            barrier()
+            ctx.barrier()
             t_a = time.perf_counter()
-            step_e2e()
+            m["step_e2e"]()
             lat.append((time.perf_counter() - t_a) * 1e6)
         lat.sort()
         latency = {"calls": len(lat), "p50_us": lat[len(lat) // 2], "p99_us": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                    "min_us": lat[0], "what": "wall clock around one host-buffer search call (H2D + search + merge + D2H + sync)"}
-
-    if rank == 0:
-        ms_per_step = total_ms / args.steps
-        value = args.nq / (ms_per_step / 1e3)
-        e2e_value = args.nq / (e2e_ms / args.steps / 1e3)
-        peaks = {}
-        peaks_src = "fallback"
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-            peaks_src = "measured"
-        except Exception:
-            pass
-        kern_ms = tot.value / max(1, nl.value)
-        local_rows = r1 - r0
-        # f32x3: six bf16 product terms per fp32 product on the tensor pipe, 12 stored bytes per element
-        terms = 6 if args.dtype == "f32x3" else 1
-        flops = 2.0 * args.nq * local_rows * args.dim * terms
-        bytes_ = local_rows * args.dim * {"f32": 4, "f32x3": 12}.get(args.dtype, 2) + args.nq * args.dim * 2 * terms + args.nq * k * 12
-        ridge_tensor = args.nq * terms > 211 and args.dtype != "f32"
-        if args.dtype == "f32":
-            # exact mode is SIMT FFMA-bound: 148 SMs x 128 FMA/clk x 2 flop at the max SM clock (no measured peak for it)
-            peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-            roof = {"bound": "fp32-ffma", "achieved": flops / (kern_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s"}
-        elif ridge_tensor:
-            peak = float(peaks.get("bf16_tflops", 1590.0))
-            roof = {"bound": "tensor", "achieved": flops / (kern_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s"}
-            if terms > 1:
-                roof["note"] = "bf16 tensor flops issued (6 product terms per fp32 product); fp32-equivalent rate = achieved / 6"
-        else:
-            peak = float(peaks.get("hbm_gbs", 6650.0))
-            roof = {"bound": "hbm", "achieved": bytes_ / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["peak_source"] = f"{peaks_src} (MEASURED_PEAKS.json burst figure: kernel timed alone)" if peaks_src == "measured" else "fallback (B200_PROFILING.md)"
-        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch(es), from the committed
-        # `ncu --set full` capture of this same workload (profiles/traffic.json); null for other workloads
-        roof["traffic"] = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tr = json.load(f)
-            key = f"nq{args.nq}_rows{args.rows}_d{args.dim}_{args.dtype}_gpus{world}"
-            if key in tr:
-                roof["traffic"] = tr[key]["dram_bytes_per_launch"]
-                roof["traffic_source"] = tr[key]["source"]
-        except Exception:
-            pass
-        roof["kernel"] = {"f32": "f32_topk_kernel"}.get(args.dtype, "stream_topk_kernel" if (args.variant == "stream" and args.nq <= 32) else "tc_topk_kernel")
-        roof["timed_region"] = "all contraction passes of a step (threshold-priming passes + main pass) and their merge kernels; excludes only the query cast"
-        roof["kernel_ms"] = kern_ms
-        roof["kernel_launches_timed"] = nl.value
-        roof["algorithmic"] = {"flops_per_launch": flops, "bytes_per_launch": bytes_}
+    line = None
+    if ctx.rank == 0:
+        roof = roofline(args, args.dtype, args.nq, m["local_rows"], m["kernel_ms"], ctx.world, args.rows)
+        roof["kernel_launches_timed"] = m["kernel_launches_timed"]
         line = {
-            "metric": "queries/s exact top-100 over 12Mx768 passages", "value": value, "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "metric": METRIC, "value": args.nq / (m["ms_per_step"] / 1e3), "unit": "queries/s", "n_gpus": ctx.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, world),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": args.nq * args.dim * 4,
-                    "d2h_bytes_per_step": args.nq * k * 12, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches_timed,
+            "config": workload_config(args, ctx.world),
+            "clocks": m["clocks"],
+            "e2e": {"value": args.nq / (m["e2e_ms_per_step"] / 1e3), "unit": "queries/s", "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"], "ms_per_step": m["e2e_ms_per_step"],
+                    "what": ("vq_index_search_host: pinned host f32 queries in, host (scores, ids) out" if ctx.world == 1 else
+                             "ShardedFlatIndex.search_host: every rank uploads its query slice, all-gather, search + exchange + merge, rank 0 reads back")},
+            "gpu_launches": m["launches"],
             "roofline": roof,
         }
+        line.update(result_digest(m["scores"], m["ids"]))
+        if not args.no_parity_check:
+            try:
+                line["parity_check"] = parity_check(args, ctx, m["scores"], m["ids"], m["q_dev"])
+            except Exception as e:  # never sink the measured numbers
+                line["parity_check"] = {"ok": False, "error": repr(e)}
         if latency is not None:
             line["latency"] = latency
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                times, scale, cores, sample_rows = cpu_port_sample(args, device, args.cpu_sample_rows or 1_500_000, repeats=1, warmup=0)
-                step_s = times[0] * scale
-                line["cpu_baseline"] = {
-                    "value": args.nq / step_s, "unit": "queries/s", "cores": cores, "kind": "port",
-                    "sample": f"all {args.nq} queries x first {sample_rows} of {args.rows} rows (fp32 upcast of the same values), 1 pass, time scaled x{scale:.2f}",
-                    "sample_ms": times[0] * 1e3}
-            except Exception as e:  # the CPU leg must never sink the GPU numbers
-                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    # free the main index before the secondary modes / the CPU leg
+    m["index"].close()
+    m_small = {key: m[key] for key in ("ms_per_step",)}
+    del m
+    torch.cuda.empty_cache()
+    if not args.no_modes and args.config in (1, 4):
+        modes = {}
+        if args.config == 1:
+            plan = [("f32", args.nq, args.steps), ("bf16", args.nq, args.steps)]
+        else:
+            # fp32-exact on an 8,192-query slice (SURVEY §8d config 4): 3 s per step on the SIMT pipe
+            plan = [("f16", args.nq, args.steps), ("f32", min(args.nq, 8192), 1)]
+        for dtype, nq, steps in plan:
+            if dtype == args.dtype:
+                continue
+            mm = measure_search(args, ctx, dtype, nq, args.rows, steps, 3 if steps > 1 else 1, with_e2e=False)
+            if ctx.rank == 0:
+                r = roofline(args, dtype, nq, mm["local_rows"], mm["kernel_ms"], ctx.world, args.rows)
+                modes[dtype] = {"nq": nq, "steps": steps, "ms_per_step": mm["ms_per_step"], "queries_per_s": nq / (mm["ms_per_step"] / 1e3),
+                                "roofline": {key: r[key] for key in ("bound", "achieved", "peak", "unit", "frac")}}
+                modes[dtype].update(result_digest(mm["scores"], mm["ids"]))
+            mm["index"].close()
+            del mm
+            torch.cuda.empty_cache()
+        if ctx.rank == 0:
+            line["modes"] = modes
+    if ctx.rank == 0:
+        if ctx.world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args, ctx)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    return m_small
+
+
+def cpu_baseline_leg(args, ctx):
+    try:
+        port = CpuPort(args, ctx.device, force_rows=args.cpu_sample_rows)
+        port.step()  # untimed: page in the host copy, spin up the BLAS threads
+        t = [port.step() for _ in range(2 if not port.extrapolated else 1)]
+        step_s = sum(t) / len(t)
+        return {"value": port.queries_per_s(step_s), "unit": "queries/s", "cores": port.cores, "kind": "port",
+                "sample": port.describe(len(t)), "sample_ms": step_s * 1e3, "extrapolated": port.extrapolated}
+    except Exception as e:  # the CPU leg must never sink the GPU numbers
+        return {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+
+
+# ----------------------------------------------------------------------------- config 5: latency regime
+def run_latency_config(args, ctx):
+    """Per-call device latency of batch 1..32 searches over the (sharded) 12M-row corpus: `warmup` calls then `steps`
+    calls per batch size, each bracketed by CUDA events, CUDA-graph replay on one GPU.  With N GPUs a call is local
+    search + exchange + cross-shard merge, timed on every rank (max over ranks of the percentiles)."""
+    import torch
+
+    index, sharded, (r0, r1) = build_shard(ctx, args.rows, args.dim, args.dtype, args.variant)
+    dt = torch_dtype(args.dtype)
+    k = args.k
+    peaks, _ = load_peaks()
+    hbm = float(peaks.get("hbm_gbs", 6650.0)) * 1e9
+    floor_us = (r1 - r0) * args.dim * 2 / hbm * 1e6
+    table, digests = [], {}
+    batch_sizes = [n for n in (1, 2, 4, 8, 16, 32) if n <= max(1, args.nq)]
+    q_all = gen_queries(32, args.dim, ctx.device, dt)
+    for nq in batch_sizes:
+        q = q_all[:nq].contiguous()
+        if sharded is None:
+            cap = index.capture_search(nq, k, query_dtype=dt)
+            cap.queries.copy_(q)
+            call = cap.replay
+        else:
+            cap = sharded.capture_search(nq, k, query_dtype=dt) if hasattr(sharded, "capture_search") else None
+            if cap is not None:
+                cap.queries.copy_(q)
+                call = cap.replay
+            else:
+                call = lambda q=q: sharded.search_tensors(q, k)  # noqa: E731
+        for _ in range(args.warmup):
+            call()
+        ctx.barrier()
+        lat = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call()
+            e1.record()
+            e1.synchronize()
+            lat.append(e0.elapsed_time(e1) * 1e3)
+        lat.sort()
+        p50 = ctx.max_over_ranks(lat[len(lat) // 2])
+        p99 = ctx.max_over_ranks(lat[min(len(lat) - 1, int(len(lat) * 0.99))])
+        mean = ctx.max_over_ranks(sum(lat) / len(lat))
+        s, i = call()
+        torch.cuda.synchronize()
+        table.append({"nq": nq, "p50_us": round(p50, 1), "p99_us": round(p99, 1), "mean_us": round(mean, 1),
+                      "queries_per_s": round(nq / p50 * 1e6, 1), "hbm_frac_p50": round(floor_us / p50, 4)})
+        if ctx.rank == 0:
+            digests[str(nq)] = result_digest(s, i)["result_sha"]
+        del cap
+    # end-to-end: host-buffer call wall clock at the largest batch size
+    nq = batch_sizes[-1]
+    q_host = q_all[:nq].float().cpu().pin_memory()
+    out_s = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    out_i = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    from viquae_b200 import _lib
+    lib = _lib.load()
+
+    def step_e2e():
+        if sharded is None:
+            _lib.check(lib.vq_index_search_host(index._h, q_host.data_ptr(), nq, 0, k, out_s.data_ptr(), out_i.data_ptr()))
+        else:
+            sharded.search_host(q_host, k, out=(out_s, out_i), result_ranks=0)
+            torch.cuda.current_stream().synchronize()
+    e2e_ms, _, _ = ctx.timed(step_e2e, min(args.steps, 200), 10)
+    e2e_ms /= min(args.steps, 200)
+    if ctx.rank == 0:
+        last = table[-1]
+        line = {
+            "metric": METRIC, "value": last["queries_per_s"], "unit": "queries/s", "n_gpus": ctx.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": last["p50_us"] / 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, ctx.world),
+            "latency": {"per_batch_size": table, "calls_per_batch_size": args.steps, "warmup_calls": args.warmup,
+                        "what": "device time of one call (CUDA events around a graph replay / the sharded step incl. exchange + merge); p50/p99 = max over ranks",
+                        "hbm_floor_us_per_shard": round(floor_us, 1)},
+            "e2e": {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4, "d2h_bytes_per_step": nq * k * 12,
+                    "ms_per_step": e2e_ms, "what": f"host-buffer call at nq={nq}"},
+            "gpu_launches": None,
+            "roofline": {"bound": "hbm", "achieved": (r1 - r0) * args.dim * 2 / (last["p50_us"] * 1e-6) / 1e9, "peak": hbm / 1e9, "unit": "GB/s",
+                         "frac": last["hbm_frac_p50"], "traffic": None, "kernel": "tc_topk_kernel<1>",
+                         "note": "whole call (all passes + merges + exchange) against the shard's HBM stream time"},
+            "result_sha_per_batch_size": digests,
+        }
+        print(json.dumps(line), flush=True)
+    index.close()
+
+
+# ----------------------------------------------------------------------------- config 3: multimodal fusion pipeline
+def run_fusion_config(args, ctx):
+    """text (rows x 768, Flat) + image (1,495,352 x 512, L2norm,Flat) + face (506,237 x 512, L2norm,Flat, ~half of the
+    queries None), top-100 per index, article->passage expansion of the image/face hits (CSR, 1..15 passages per
+    article), default-minimum + gzmuv + weighted sum: K0/K3/K4 -> K6 -> K5, device resident, one GPU."""
+    import numpy as np
+    import torch
+    from viquae_b200.fuse import fuse_dense
+    from viquae_b200.index import B200FlatIndex
+    from viquae_b200.postprocess import CSRMapping, expand_hits
+
+    if ctx.world > 1:
+        raise SystemExit("bench.py --config 3 runs on one GPU (the small image/face indexes do not shard)")
+    dev, k, nq = ctx.device, args.k, args.nq
+
+    def build(rows, d, factory, seed):
+        idx = B200FlatIndex(d=d, dtype="bf16", string_factory=factory, capacity=rows, device=ctx.local_rank)
+        for c0 in range(0, rows, CHUNK_ROWS):
+            g = torch.Generator(device=dev)
+            g.manual_seed(seed + c0)
+            idx.add(torch.randn((min(CHUNK_ROWS, rows - c0), d), generator=g, device=dev).to(torch.bfloat16))
+        return idx
+
+    text = build(args.rows, 768, "Flat", 1)
+    image = build(1_495_352, 512, "L2norm,Flat", 2)
+    face = build(506_237, 512, "L2norm,Flat", 3)
+    g = torch.Generator(device=dev)
+    g.manual_seed(QUERY_SEED)
+    q_text = torch.randn((nq, 768), generator=g, device=dev)
+    q_img = torch.randn((nq, 512), generator=g, device=dev)
+    has_face = torch.rand((nq,), generator=g, device=dev) < 0.5
+    q_face = torch.randn((int(has_face.sum()), 512), generator=g, device=dev)
+    face_rows = torch.nonzero(has_face).flatten()
+    rng = np.random.default_rng(0)
+    deg = rng.integers(1, 16, size=1_495_352)
+    off = np.zeros(len(deg) + 1, np.int64)
+    np.cumsum(deg, out=off[1:])
+    mapping = CSRMapping.__new__(CSRMapping)
+    mapping.n_rows, mapping.max_degree = len(deg), int(deg.max())
+    mapping.offsets = torch.from_numpy(off).to(dev)
+    mapping.targets = torch.arange(int(off[-1]), device=dev, dtype=torch.int64) % args.rows
+    weights = [0.4, 0.3, 0.3]
+    q_hosts = [t.float().cpu().pin_memory() for t in (q_text, q_img, q_face)]
+
+    def pipeline(qt, qi, qf, ev=None):
+        if ev:
+            ev[0].record()
+        s_t, i_t = text.search_tensors(qt, k)
+        s_i, i_i = image.search_tensors(qi, k)
+        s_f, i_f = face.search_tensors(qf, k)
+        if ev:
+            ev[1].record()
+        r_t = expand_hits(s_t, i_t, None, None, k)
+        r_i = expand_hits(s_i, i_i, mapping, None, k)
+        r_f = expand_hits(s_f, i_f, mapping, None, k)
+        cap = max(r_t[0].shape[1], r_i[0].shape[1], r_f[0].shape[1])
+        S = torch.zeros((3, nq, cap), dtype=torch.float64, device=dev)
+        I = torch.full((3, nq, cap), -1, dtype=torch.int64, device=dev)
+        S[0, :, :r_t[0].shape[1]], I[0, :, :r_t[1].shape[1]] = r_t[0], r_t[1]
+        S[1, :, :r_i[0].shape[1]], I[1, :, :r_i[1].shape[1]] = r_i[0], r_i[1]
+        S[2, face_rows, :r_f[0].shape[1]], I[2, face_rows, :r_f[1].shape[1]] = r_f[0], r_f[1]
+        if ev:
+            ev[2].record()
+        out = fuse_dense(S, I, weights, norm="gzmuv", defmin=True)
+        if ev:
+            ev[3].record()
+        return out
+
+    def step_device():
+        return pipeline(q_text, q_img, q_face)
+
+    def step_e2e():
+        qs = [h.to(dev, non_blocking=True) for h in q_hosts]
+        fs, fi, fc = pipeline(*qs)
+        return fs.cpu(), fi.cpu(), fc.cpu()
+
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    total_ms, t0, t1 = ctx.timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop(t0, t1)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(5)]
+    for e in evs:
+        pipeline(q_text, q_img, q_face, e)
+    torch.cuda.synchronize()
+    stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in evs]).mean(0)
+    e2e_ms, _, _ = ctx.timed(step_e2e, args.steps, args.warmup)
+    fs, fi, fc = step_device()
+    torch.cuda.synchronize()
+    ms = total_ms / args.steps
+    flops = 2.0 * nq * (args.rows * 768 + 1_495_352 * 512) + 2.0 * q_face.shape[0] * 506_237 * 512
+    peaks, src = load_peaks()
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    line = {
+        "metric": METRIC, "value": nq / (ms / 1e3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 search, f64 fusion", "data": "synthetic",
+        "config": {"workload": f"text {args.rows}x768 Flat + image 1495352x512 L2norm,Flat + face 506237x512 L2norm,Flat (~50% None), {nq} queries, "
+                               f"top-{k} per index, article->passage expansion, defmin + gzmuv + wsum {weights}",
+                   "baseline_config": "configs[2] multimodal fusion", "rows": args.rows, "nq": nq, "k": k,
+                   "l2_policy": "inputs_larger_than_L2"},
+        "clocks": clocks,
+        "stages_ms": {"search": float(stage[0]), "expand": float(stage[1]), "fuse": float(stage[2])},
+        "e2e": {"value": nq / (e2e_ms / args.steps / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in q_hosts)), "d2h_bytes_per_step": int(fs.numel() * 8 + fi.numel() * 8 + fc.numel() * 4),
+                "what": "host f32 queries of the three indexes in, host fused run (scores f64, ids i64, counts) out"},
+        "gpu_launches": None,
+        "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "tc_topk_kernel (three searches) + expand_hits + fuse",
+                     "peak_source": src, "note": "whole pipeline time against the three contractions' flops"},
+        "fused_union_mean": float(fc.float().mean().item()),
+        "result_sha": hashlib.sha256(fi.cpu().numpy().tobytes() + fs.cpu().numpy().tobytes()).hexdigest()[:16],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    ctx = Ctx()
+    try:
+        if args.config == 3:
+            run_fusion_config(args, ctx)
+        elif args.config == 5:
+            run_latency_config(args, ctx)
+        else:
+            run_search_config(args, ctx)
+    finally:
+        ctx.close()
 
 
 def main():

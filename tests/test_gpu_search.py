@@ -280,15 +280,21 @@ def test_hf_dataset_dispatch_and_dataset_search_with_fusion(tmp_path):
 
 
 @pytest.mark.parametrize("many2one", [None, "max"])
-def test_gpu_postprocessing_equals_reference_loop(many2one):
+@pytest.mark.parametrize("score_range", ["dpr", "cosine"])
+def test_gpu_postprocessing_equals_reference_loop(many2one, score_range):
     """K6 (vq_expand_hits) vs the Python restatement of Searcher.__call__'s loop (search.py:413-440), including
-    overlapping mappings (dict overwrite / max semantics), early stop at k and padded hits."""
+    overlapping mappings (dict overwrite / max semantics), early stop at k and padded hits.  "cosine": scores in
+    [0, 1] as the `L2norm,Flat` indexes return them, where the reference's 1e-8 per-passage penalty is visible in
+    float32 and must be reproduced bit for bit."""
     from viquae_b200.postprocess import CSRMapping, expand_hits
     from viquae_b200.search import Searcher
     rng = np.random.default_rng(2)
     n_rows, nq, k = 500, 64, 20
     mapping = {r: sorted(rng.choice(300, size=int(rng.integers(0, 6)), replace=False).tolist()) for r in range(n_rows)}
-    scores = np.sort(rng.normal(70, 2, size=(nq, k)).astype(np.float32), axis=1)[:, ::-1].copy()
+    raw = rng.normal(70, 2, size=(nq, k)) if score_range == "dpr" else rng.uniform(0.0, 1.0, size=(nq, k))
+    scores = np.sort(raw.astype(np.float32), axis=1)[:, ::-1].copy()
+    if score_range == "cosine":
+        scores[3, 4] = scores[3, 3]  # an exact tie between two articles
     ids = np.stack([rng.choice(n_rows, size=k, replace=False) for _ in range(nq)]).astype(np.int64)
     ids[5, 7:] = -1  # a row with fewer than k hits
     scores[5, 7:] = np.finfo(np.float32).min
@@ -448,6 +454,37 @@ def test_faiss_flat_file_interchange(tmp_path):
     faiss_io.write_flat_index(tmp_path / "l2.faiss", emb, metric_type=1)
     with pytest.raises(ValueError, match="inner-product only"):
         B200FlatIndex.load(tmp_path / "l2.faiss")
+    # What the reference leaves on disk when `device` is set (search.py:237-248): the column pre-normalised in Python,
+    # "L2norm" stripped from the factory -> a PLAIN Flat file; the config still says "L2norm,Flat", and that flag (not
+    # the file's) decides that queries get normalised.
+    unit = emb / np.linalg.norm(emb, axis=1, keepdims=True)
+    faiss_io.write_flat_index(tmp_path / "stripped.faiss", unit, l2norm=False)
+    kb = KnowledgeBase(dataset=DictDS({"e": emb}), index_kwargs={"x": {"column": "e", "key": "q", "string_factory": "L2norm,Flat", "metric_type": 0,
+                                                                       "dtype": "f32", "load": True, "file": str(tmp_path / "stripped.faiss")}})
+    assert kb.indexes["x"].do_L2norm is True and kb._engines["x"].do_L2norm is True
+    s3, i3 = kb.search_batch("x", q * 7.5, k=20)   # unnormalised queries: scores must come back as cosines
+    Dr, Ir = c_oracle.flat_ip(flat_ip.l2norm(q * 7.5), unit.astype(np.float32), 20)
+    assert np.array_equal(np.asarray(i3), Ir) and np.allclose(s3, Dr, rtol=1e-5, atol=1e-6) and np.abs(s3).max() <= 1.0 + 1e-5
+
+
+def test_zero_norm_corpus_row_keeps_faiss_semantics():
+    """`"L2norm,Flat"` on the CPU path is FAISS's NormalizationTransform, which leaves a zero vector untouched: the row
+    scores 0 and stays retrievable.  Only the query side follows numpy's q / ||q|| (zero query -> NaN scores, nothing
+    selected), meerqat/ir/search.py:43-46."""
+    from viquae_b200.index import B200FlatIndex
+    rng = np.random.default_rng(4)
+    emb = rng.standard_normal((300, 32)).astype(np.float32)
+    emb[17] = 0.0
+    for dtype in ("f32", "bf16", "f32x3"):
+        idx = B200FlatIndex(d=32, dtype=dtype, string_factory="L2norm,Flat")
+        idx.add(emb)
+        rows = idx.reconstruct_n(17, 1, "f32")
+        assert np.array_equal(rows, np.zeros((1, 32), np.float32)), dtype
+        q = -emb[[3]]  # every cosine but row 17's is what it is; ask for all rows so that the zero row must appear
+        res = idx.search_batch(q, k=300)
+        ids = np.asarray(res.total_indices)[0]
+        assert 17 in ids and np.asarray(res.total_scores)[0][list(ids).index(17)] == 0.0, dtype
+        idx.close()
 
 
 @pytest.mark.parametrize("dtype,N,nq,d,k", [("bf16", 30000, 140, 256, 129), ("bf16", 50000, 40, 768, 1000), ("f16", 3000, 9, 64, 300),

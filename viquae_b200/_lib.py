@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libviquae_b200.so")
+# VIQUAE_B200_LIB points at another build of the same ABI (A/B runs of a kernel change on one box)
+LIB_PATH = os.environ.get("VIQUAE_B200_LIB") or os.path.join(_HERE, "libviquae_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 F32X3 = 3  # storage only: fp32 values split into three bf16 terms, tensor-core contraction at fp32 fidelity

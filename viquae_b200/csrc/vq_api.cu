@@ -28,6 +28,27 @@ static int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(VQ_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// Every entry point that works on an index makes the index's device current for the duration of the call and
+// restores the caller's device afterwards (an index on cuda:1 must not silently switch a cuda:0 caller).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        err = cudaGetDevice(&cur);
+        if (err == cudaSuccess && cur != dev) {
+            err = cudaSetDevice(dev);
+            if (err == cudaSuccess) prev = cur;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define VQ_ON_DEVICE(dev)                                                                                      \
+    DeviceGuard guard__(dev);                                                                                  \
+    if (guard__.err != cudaSuccess) return fail(VQ_ERR_CUDA, "cudaSetDevice(%d): %s", (dev), cudaGetErrorString(guard__.err))
+
 #define VQ_TIMING_SLOTS 256
 
 struct vq_index {
@@ -145,7 +166,7 @@ int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capac
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(VQ_ERR_INVALID, "vq_index_create: device %d not in [0, %d)", device, ndev);
-    CUDA_TRY(cudaSetDevice(device));
+    VQ_ON_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(VQ_ERR_UNSUPPORTED, "viquae_b200 needs an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
@@ -187,7 +208,7 @@ int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capac
 
 void vq_index_destroy(vq_index* idx) {
     if (!idx) return;
-    cudaSetDevice(idx->device);
+    DeviceGuard guard(idx->device);
     if (idx->data) cudaFree(idx->data);
     if (idx->hws) cudaFree(idx->hws);
     ingest_release(idx);
@@ -217,7 +238,7 @@ int vq_index_set_variant(vq_index* idx, int variant) {
 
 int vq_index_set_timing(vq_index* idx, int enable) {
     if (!idx) return fail(VQ_ERR_INVALID, "null index");
-    CUDA_TRY(cudaSetDevice(idx->device));
+    VQ_ON_DEVICE(idx->device);
     if (enable && !idx->timing) {
         for (int i = 0; i < VQ_TIMING_SLOTS; i++) {
             CUDA_TRY(cudaEventCreate(&idx->ev0[i]));
@@ -288,13 +309,13 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
     // rows are uint32 in the candidate keys and int32 TMA coordinates in the tensor-core kernel
     if (idx->ntotal + n > 0x7FFFFF00ull) return fail(VQ_ERR_UNSUPPORTED, "vq_index_add: more than 2^31-256 rows per shard");
     cudaStream_t s = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(idx->device));
+    VQ_ON_DEVICE(idx->device);
     int rc = grow(idx, idx->ntotal + n, s);
     if (rc) return rc;
     const size_t row = (size_t)idx->ld * esize(idx->dtype);
     uint8_t* dst = (uint8_t*)idx->data + idx->ntotal * row;
     if (is_device_ptr(x)) {
-        rc = to_storage(idx, x, src_dtype, dst, (long long)n, l2norm, 0, s);
+        rc = to_storage(idx, x, src_dtype, dst, (long long)n, l2norm ? 2 : 0, 0, s);
         if (rc) return fail(VQ_ERR_CUDA, "vq_index_add: prep kernel launch failed (%d)", rc);
     } else {
         // host source: pageable rows -> pinned buffer (host threads) -> device staging (DMA) -> conversion kernel,
@@ -317,7 +338,7 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
                 e = cudaMemcpyAsync(idx->stage[b], idx->pin[b], m * src_row, cudaMemcpyHostToDevice, s);
             }
             if (e == cudaSuccess) {
-                rc = to_storage(idx, idx->stage[b], src_dtype, dst + r0 * row, (long long)m, l2norm, 0, s);
+                rc = to_storage(idx, idx->stage[b], src_dtype, dst + r0 * row, (long long)m, l2norm ? 2 : 0, 0, s);
                 if (rc == 0) e = cudaEventRecord(idx->ingest_ev[b], s);
             }
             if (e != cudaSuccess || rc) {
@@ -335,7 +356,7 @@ int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* ds
     if (!idx || (!dst && n) || !dtype_ok(dst_dtype) || start + n > idx->ntotal) return fail(VQ_ERR_INVALID, "vq_index_copy_rows: bad arguments");
     if (n == 0) return VQ_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(idx->device));
+    VQ_ON_DEVICE(idx->device);
     const size_t row = (size_t)idx->ld * esize(idx->dtype);
     const uint8_t* src = (const uint8_t*)idx->data + start * row;
     if (is_device_ptr(dst)) {
@@ -562,7 +583,7 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     if (!q || !out_scores || !out_ids || !workspace) return fail(VQ_ERR_INVALID, "vq_index_search: null pointer");
     if (k > VQ_KMAX_BANDED) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: k=%d > %d is not served", k, VQ_KMAX_BANDED);
     cudaStream_t s = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(idx->device));
+    VQ_ON_DEVICE(idx->device);
     SearchPlan sp;
     make_plan(idx, nq, &sp);
     if (k > VQ_KMAX && sp.kind == 2) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: the streaming variant serves k <= %d", VQ_KMAX);
@@ -570,7 +591,7 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     if (workspace_bytes < need) return fail(VQ_ERR_NOMEM, "vq_index_search: workspace %zu < %zu bytes", workspace_bytes, need);
     uint8_t* ws = (uint8_t*)workspace;
     void* qprep = ws + sp.off_q;
-    int rc = to_storage(idx, q, q_dtype, qprep, nq, l2norm_q, 1, s);
+    int rc = to_storage(idx, q, q_dtype, qprep, nq, l2norm_q ? 1 : 0, 1, s);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
     idx->launches += 1;
     // rows [nq, nq_pad) of the prepared query matrix are real zero rows, so the tensor-core path never
@@ -611,7 +632,7 @@ int vq_index_search_host(vq_index* idx, const float* q_host, int nq, int l2norm_
     if (!idx || nq < 0 || k < 1) return fail(VQ_ERR_INVALID, "vq_index_search_host: bad arguments");
     if (nq == 0) return VQ_OK;
     if (!q_host || !out_scores_host || !out_ids_host) return fail(VQ_ERR_INVALID, "vq_index_search_host: null pointer");
-    CUDA_TRY(cudaSetDevice(idx->device));
+    VQ_ON_DEVICE(idx->device);
     SearchPlan sp;
     make_plan(idx, nq, &sp);
     const size_t q_bytes = align256((size_t)nq * idx->d * sizeof(float));

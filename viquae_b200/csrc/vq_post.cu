@@ -8,9 +8,11 @@
 //         if len(run) >= k: break
 //
 // The run is a Python dict: documents keep INSERTION order and duplicates update in place; that order is part
-// of the contract (ties are later sorted stably).  The 1e-8 penalty is below float32 resolution at DPR score
-// magnitudes and, under NumPy >= 2 promotion rules, `np.float32 - 1e-8` stays float32: passages of one article
-// tie with the article's score and keep mapping order — which is exactly what insertion order preserves here.
+// of the contract (ties are later sorted stably).  The penalty is carried exactly like the reference does under
+// NumPy >= 2 promotion rules: it accumulates in double (a Python float), restarts at 0 for every hit, is
+// converted to float32 and subtracted in float32 (`np.float32 - float` stays float32).  At DPR score magnitudes
+// (~70, ulp 7.6e-6) the subtraction is a no-op; for cosine scores (`L2norm,Flat` indexes, |s| <= 1, ulp <= 6e-8)
+// it separates the passages of one article, as in the reference.
 //
 // One warp per query; the growing run lives in shared memory; membership tests are warp-parallel.
 // The mapping is CSR on the device: offsets int64 [n_rows + 1], targets int64 [nnz].
@@ -40,6 +42,7 @@ expand_hits_kernel(const float* __restrict__ scores, const long long* __restrict
         const float s = scores[(size_t)q * k_in + h];
         const long long t0 = map_offsets ? map_offsets[row] : row;
         const long long t1 = map_offsets ? map_offsets[row + 1] : row + 1;
+        double penalty = 0.0;  // search.py:420: reset per hit; only the one2many mapping path uses it
         for (long long t = t0; t < t1; t++) {
             const long long doc = map_offsets ? map_targets[t] : row;
             // is doc already in the run?  (warp-parallel scan, lowest matching position wins)
@@ -49,12 +52,15 @@ expand_hits_kernel(const float* __restrict__ scores, const long long* __restrict
                 const unsigned m = __ballot_sync(VQ_FULL_MASK, i < n && docs[i] == doc);
                 if (m) { found = base + __ffs(m) - 1; break; }
             }
+            // one2many through a mapping: score - penalty (float32 arithmetic); many2one / no mapping: the score
+            const float v = (map_offsets && !many2one_max) ? __fsub_rn(s, (float)penalty) : s;
+            penalty += 1e-8;
             if (lane == 0) {
                 if (found >= 0) {
-                    if (!many2one_max || vals[found] < s) vals[found] = s;
+                    if (!many2one_max || vals[found] < v) vals[found] = v;
                 } else if (n < out_cap) {
                     docs[n] = doc;
-                    vals[n] = s;
+                    vals[n] = v;
                 }
             }
             if (found < 0) {

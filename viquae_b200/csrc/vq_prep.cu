@@ -1,8 +1,10 @@
 // K0 — ingest / query preparation: dtype conversion with optional row-wise L2 normalisation.
 //
 // Replaces the reference's numpy L2norm (meerqat/ir/search.py:43-46: q / ||q||_2, no epsilon, so a
-// zero row becomes NaN exactly like the reference) and FAISS's NormalizationTransform for
-// "L2norm,Flat" (search.py:230-245), fused with the fp32 -> bf16/fp16 cast of the storage dtype.
+// zero row becomes NaN exactly like the reference; l2norm == 1, the query side) and FAISS's
+// NormalizationTransform for "L2norm,Flat" (search.py:230-245; fvec_renorm_L2 leaves a zero vector
+// untouched, so such a corpus row scores 0 instead of becoming unretrievable; l2norm == 2, the ingest
+// side), fused with the fp32 -> bf16/fp16 cast of the storage dtype.
 // One warp per row, lane-strided (fully coalesced) element loads/stores; HBM-bound and off the search path's
 // critical section (runs once per ingest batch and once per query batch).
 #include "vq_common.cuh"
@@ -37,12 +39,13 @@ prep_rows_kernel(const S* __restrict__ src, long long ld_src, D* __restrict__ ds
 #pragma unroll
             for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(VQ_FULL_MASK, acc, o2);
             inv_is_div = sqrtf(acc);
+            if (l2norm == 2 && inv_is_div == 0.0f) inv_is_div = 1.0f;  // FAISS: zero vectors stay zero
         }
         for (int j = lane; j < (int)ld_dst; j += 32) {
             float v = 0.0f;
             if (j < d) {
                 v = to_f32<S>(s[j]);
-                if (l2norm) v = v / inv_is_div;  // 0/0 -> NaN like numpy
+                if (l2norm) v = v / inv_is_div;  // l2norm == 1: 0/0 -> NaN like numpy
             }
             o[j] = from_f32<D>(v);
         }
@@ -100,6 +103,7 @@ split_rows_kernel(const S* __restrict__ src, long long ld_src, __nv_bfloat16* __
 #pragma unroll
             for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(VQ_FULL_MASK, acc, o2);
             div = sqrtf(acc);
+            if (l2norm == 2 && div == 0.0f) div = 1.0f;
         }
         for (int j = lane; j < seg; j += 32) {
             float v = 0.0f;

@@ -94,6 +94,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// one lane of a converged warp (the instruction needs warp-uniform control flow around it)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const void* p) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(p) : "memory");
 }
@@ -350,30 +362,38 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         }
                     }
                 }
-                if (lane == 0) {
-                    const int x_row0 = phys_tile(p, t) * BLOCK_N + (int)rank * C::LOAD_N;
-                    for (int kb = 0; kb < num_kb; kb++) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                // the whole warp runs the k loop with warp-uniform state; one elected lane issues the copies, so the
+                // descriptors, coordinates and barrier addresses stay in uniform registers
+                const int x_row0 = phys_tile(p, t) * BLOCK_N + (int)rank * C::LOAD_N;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one()) {
                         tma_load_2d<CG>(&tmap_q, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, q_row0,
                                         0x14F0000000000000ull /*evict last: queries are re-read by every tile*/);
                         tma_load_2d<CG>(&tmap_x, &full_bar[stage], smem_b + stage * C::B_STAGE_BYTES, kb * BLOCK_K, x_row0,
                                         0x1000000000000000ull /*evict normal*/);
                         if (leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
                         else mbar_arrive_cluster(&full_bar[stage], 0);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                stage = __shfl_sync(VQ_FULL_MASK, stage, 0);
-                phase = __shfl_sync(VQ_FULL_MASK, phase, 0);
             }
             // done with this item: never hold the others back
             if (synced && lane == 0) asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p.progress + item), "r"(0x7fffffff) : "memory");
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread of the leader CTA) =====================
-        if (leader && lane == 0) {
+        // ===================== MMA issuer (warp 1 of the leader CTA) =====================
+        // All 32 lanes run the loop with warp-uniform state and ONE elected lane issues the MMAs of a k block: shared
+        // memory descriptors, the TMEM address and the barrier addresses then live in uniform registers.  (Issued from
+        // inside an `if (lane == 0)` region the same loop costs ~115 SASS instructions per k block — a waterfall of
+        // ELECT / R2UR.BROADCAST around every UTCHMMA — which is as long as the 4 MMAs themselves take: the tensor
+        // pipe sat at 84 % active, paced by its own issuer.)
+        if (leader) {
             const uint32_t idesc = p.idesc_base | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((BLOCK_Q * CG) >> 4) << 24);
+            const uint64_t adesc0 = make_smem_desc(smem_u32(smem_a));
+            const uint64_t bdesc0 = make_smem_desc(smem_u32(smem_b));
             uint32_t stage = 0, phase = 0, iter = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
                 const int chunk = item / p.m_tiles;
@@ -386,21 +406,24 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     for (int kb = 0; kb < num_kb; kb++) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-                        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
-#pragma unroll
-                        for (int k4 = 0; k4 < BLOCK_K / UMMA_K; k4++) {
+                        if (elect_one()) {
+                            // stage s of an operand ring starts s * STAGE_BYTES further: + (bytes >> 4) in the address field
+                            const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+                            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (C::B_STAGE_BYTES >> 4));
                             // +32 B per UMMA_K inside the swizzle atom = +2 in the (addr >> 4) field
-                            umma_f16<CG>(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc, (uint32_t)((kb | k4) != 0));
+                            umma_f16<CG>(tmem_d, adesc, bdesc, idesc, (uint32_t)(kb != 0));
+#pragma unroll
+                            for (int k4 = 1; k4 < BLOCK_K / UMMA_K; k4++)
+                                umma_f16<CG>(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc, 1u);
+                            umma_commit<CG>(&empty_bar[stage]);                       // frees the smem slot (both CTAs)
+                            if (kb == num_kb - 1) umma_commit<CG>(&tmem_full_bar[as]);  // accumulator ready (both CTAs)
                         }
-                        umma_commit<CG>(&empty_bar[stage]);                       // frees the smem slot (both CTAs)
-                        if (kb == num_kb - 1) umma_commit<CG>(&tmem_full_bar[as]);  // accumulator ready (both CTAs)
+                        __syncwarp();
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-        __syncwarp();
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> registers -> threshold filter -> candidate lists =====================
         const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: the TMEM lane quarter this warp may read

@@ -244,6 +244,9 @@ class B200FlatIndex(BaseIndex):
             raise ValueError("Shape of query must be 2D")
         if queries.shape[1] != self.d:
             raise ValueError(f"dimension mismatch: index d={self.d}, queries d={queries.shape[1]}")
+        if not queries.is_cuda or queries.device.index != self.device:
+            raise ValueError(f"search_tensors needs queries on cuda:{self.device} (the index's device), got {queries.device}; "
+                             "host arrays go through search_batch")
         q = queries.contiguous()
         nq = q.shape[0]
         dev = f"cuda:{self.device}"
@@ -372,15 +375,18 @@ class CapturedSearch:
         # own workspace: the index's shared scratch buffer may be reallocated by a later, larger search
         self._ws = torch.empty((_lib.load().vq_index_workspace_bytes(index._h, nq, k),), dtype=torch.uint8, device=dev)
         self._l2 = int(index.do_L2norm if l2norm is None else bool(l2norm))
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(index.device))
-        with torch.cuda.stream(side):
-            self._launch(side)  # warm-up outside capture: one-time function attributes, lazy module load
-        torch.cuda.current_stream(index.device).wait_stream(side)
-        side.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._launch(torch.cuda.current_stream(index.device))
+        # capture on the INDEX's device, whatever the caller's current device is: torch.cuda.graph records the
+        # current device's capture stream, and launches made on another device's stream would not be captured
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(index.device))
+            with torch.cuda.stream(side):
+                self._launch(side)  # warm-up outside capture: one-time function attributes, lazy module load
+            torch.cuda.current_stream(index.device).wait_stream(side)
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch(torch.cuda.current_stream(index.device))
 
     def _launch(self, stream):
         q = self.queries

@@ -145,6 +145,11 @@ class KnowledgeBase:
             if path is None:
                 raise ValueError("load=True needs `file` (or `save_path`) pointing at a saved index")
             engine = B200FlatIndex.load(path, device=dev, variant=variant, dtype=dtype)
+            # The file only knows what its writer knew.  With `device` set the reference strips "L2norm" from the
+            # factory, pre-normalises the column and saves a plain Flat index (search.py:237-248), and normalises the
+            # queries in Python because the CONFIG says "L2norm,Flat" (Index.do_L2norm, search.py:144-145): the
+            # config's flag wins whenever it asks for normalisation.
+            engine.do_L2norm = bool(engine.do_L2norm or do_L2norm)
             if self.dataset is not None and len(engine) != len(self.dataset):
                 raise ValueError(f"Index size should match Dataset size, but Index '{index_name}' at {path} has "
                                  f"{len(engine)} elements while the dataset has {len(self.dataset)} examples.")
@@ -300,7 +305,16 @@ class Searcher:
             raise ValueError("Shape of query must be 2D")
         dev = torch.device(f"cuda:{engine.device}")
         s, ids = engine.search_tensors(torch.from_numpy(q).to(dev), self.k)
-        out_s, out_i, out_c = expand_hits(s, ids, kb.csr_mapping(engine.device), kb.many2one, self.k)
+        try:
+            out_s, out_i, out_c = expand_hits(s, ids, kb.csr_mapping(engine.device), kb.many2one, self.k)
+        except _lib.EngineError as e:
+            if e.code != _lib.ERR_UNSUPPORTED:
+                raise
+            # an article with more passages than the kernel's shared-memory run can hold: the reference's loop on the host
+            scores, indices = s.cpu().numpy(), ids.cpu().numpy()
+            for j, i in enumerate(kept):
+                self._record(kb, run[batch["id"][i]], scores[j], indices[j])
+            return
         out_s, out_i, out_c = out_s.cpu().numpy(), out_i.cpu().numpy(), out_c.cpu().numpy()
         for j, i in enumerate(kept):
             n = int(out_c[j])

@@ -71,10 +71,16 @@ class ShardedFlatIndex:
         self.dist.all_gather_into_tensor(i_all, i_m.contiguous(), group=self.group)
         return s_all[:nq], i_all[:nq]
 
-    def search_tensors(self, queries, k: int = 100):
+    def search_tensors(self, queries, k: int = 100, l2norm: Optional[bool] = None):
         """queries: the SAME [nq, d] tensor on every rank (device of the local shard).
-        Returns the global (scores [nq, k], ids [nq, k]) on every rank."""
+        Returns the global (scores [nq, k], ids [nq, k]) on every rank.  ``l2norm`` overrides the local index's
+        query normalisation (``search_host`` normalises before the queries travel)."""
         import torch
+
+        if l2norm is not None:
+            local_search = lambda q, kk, out=None: self.local_index.search_tensors(q, kk, l2norm=l2norm, out=out)  # noqa: E731
+        else:
+            local_search = None
 
         if (self.world_size > 1 and self._packed_ok and queries.shape[0] < self.SLICE_EXCHANGE_MIN_QUERIES
                 and self.dist.get_backend(self.group) == "nccl"):
@@ -82,11 +88,11 @@ class ShardedFlatIndex:
             from .index import merge_topk_packed, packed_result_buffer
             nq = queries.shape[0]
             mine, s_v, i_v = packed_result_buffer(nq, k, queries.device)
-            self.local_index.search_tensors(queries, k, out=(s_v[0], i_v[0]))
+            self.local_index.search_tensors(queries, k, l2norm=l2norm, out=(s_v[0], i_v[0]))
             gathered = torch.empty((self.world_size, mine.shape[1]), dtype=torch.uint8, device=queries.device)
             self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
             return merge_topk_packed(gathered, nq, k)
-        s_loc, i_loc = self._local_search(queries, k)
+        s_loc, i_loc = (local_search or self._local_search)(queries, k)
         if self.world_size == 1:
             return s_loc, i_loc
         nq = s_loc.shape[0]
@@ -103,14 +109,66 @@ class ShardedFlatIndex:
             self.dist.all_gather(list(i_all.unbind(0)), i_loc.contiguous(), group=self.group)
         return self._merge(s_all, i_all, k)
 
-    def search_batch(self, queries, k: int = 100):
-        """Host entry point: numpy/torch host queries [nq, d] -> numpy (scores, ids), like
-        ``KnowledgeBase.search_batch`` expects from ``Dataset.search_batch`` (meerqat/ir/search.py:146)."""
+    def _transport_dtype(self):
+        """dtype the queries travel in between ranks: the index's own 16-bit type (rounding is what the local search
+        would do anyway, and it is deterministic), full fp32 for the fp32 storage modes."""
+        import torch
+
+        name = getattr(self.local_index, "dtype", "f32")
+        return {"bf16": torch.bfloat16, "f16": torch.float16, "fp16": torch.float16, "bfloat16": torch.bfloat16,
+                "float16": torch.float16}.get(name, torch.float32)
+
+    def search_host(self, queries, k: int = 100, out=None, result_ranks="all"):
+        """Host entry point of the sharded engine: the SAME host float32 queries [nq, d] on every rank.
+
+        Rank r copies only its slice ``[r*nq/G, (r+1)*nq/G)`` to the device, casts it to the transport dtype
+        (``vq_prep_rows``) and one all-gather over NVLink rebuilds the batch on every GPU — instead of G full
+        H2D copies through the host's PCIe root.  The merged result is copied back on ``result_ranks`` ("all" or a
+        rank number; other ranks return ``None``) into ``out=(scores, ids)`` (pinned torch CPU tensors) when given.
+        Mirrors what ``KnowledgeBase.search_batch`` hands to ``Dataset.search_batch`` (meerqat/ir/search.py:146)."""
         import numpy as np
         import torch
 
-        q = torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float32))
-        dev = f"cuda:{self.local_index.device}" if self.local_index is not None else "cpu"
-        q = q.to(dev, non_blocking=True)
-        s, i = self.search_tensors(q, k)
-        return s.cpu().numpy(), i.cpu().numpy()
+        from . import _lib
+
+        q = queries if isinstance(queries, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32))
+        if q.dim() != 2:
+            raise ValueError("Shape of query must be 2D")
+        nq, d = q.shape
+        dev = torch.device(f"cuda:{self.local_index.device}")
+        G, r = self.world_size, self.rank
+        tdt = self._transport_dtype()
+        l2 = bool(getattr(self.local_index, "do_L2norm", False))
+        sliced = False
+        if G == 1 or nq < G or self.dist.get_backend(self.group) != "nccl":
+            q_all = q.to(dev, non_blocking=True)
+        else:
+            per = (nq + G - 1) // G
+            a, b = min(nq, r * per), min(nq, (r + 1) * per)
+            q_all = torch.empty((G * per, d), dtype=tdt, device=dev)
+            part = torch.zeros((per, d), dtype=tdt, device=dev)  # the last rank's slice may be short: zero rows
+            if b > a:
+                mine = q[a:b].to(dev, non_blocking=True)
+                with torch.cuda.device(dev):
+                    code = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+                    _lib.check(_lib.load().vq_prep_rows(mine.data_ptr(), code[mine.dtype], part.data_ptr(), code[tdt], b - a, d, int(l2),
+                                                        torch.cuda.current_stream(dev).cuda_stream))
+            self.dist.all_gather_into_tensor(q_all, part, group=self.group)
+            q_all = q_all[:nq]
+            sliced = True
+        # a slice was normalised in fp32 BEFORE it was rounded for transport (what a single GPU does): not again
+        s, i = self.search_tensors(q_all, k, l2norm=False if (sliced and l2) else None)
+        if result_ranks != "all" and int(result_ranks) != r:
+            return None
+        if out is not None:
+            out[0].copy_(s, non_blocking=True)
+            out[1].copy_(i, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return out
+        return s.cpu(), i.cpu()
+
+    def search_batch(self, queries, k: int = 100):
+        """numpy/torch host queries [nq, d] -> numpy (scores, ids) on every rank, like ``KnowledgeBase.search_batch``
+        expects from ``Dataset.search_batch`` (meerqat/ir/search.py:146)."""
+        s, i = self.search_host(queries, k)
+        return s.numpy(), i.numpy()
