@@ -4,7 +4,8 @@ import csv, io, subprocess, sys, collections
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum ", "dram__bytes_write.sum ", "dram__bytes_read.sum.per_second", "lts__t_sector_hit_rate.pct",
         "lts__t_sectors_srcunit_tex_op_read.sum ", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__pipe_tensor_cycles_active_realtime.avg.pct", "sm__cycles_elapsed.max ", "sm__inst_executed.sum.per_cycle_elapsed", "launch__registers_per_thread ",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct", "sm__cycles_elapsed.max ", "gpc__cycles_elapsed.max.per_second", "l1tex__m_xbar2l1tex_read_bytes.sum ",
+        "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "sm__inst_executed.sum.per_cycle_elapsed", "launch__registers_per_thread ",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ", "smsp__inst_executed.sum ",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size", "smsp__pcsamp_sample_buffer", "sm__cycles_active.avg "]
 
@@ -16,7 +17,10 @@ def raw(rep):
         name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
         print("==", name[:90])
         for h, u, v in zip(hdr, units, vals):
-            if any((h + " ").startswith(k) or k.strip() == h for k in KEYS):
+            # section-prefixed columns ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime...") carry the metric
+            # name after the last section prefix: match on that
+            base = h.split("TriageCompute.")[-1]
+            if v != "" and any((base + " ").startswith(k) or k.strip() == base for k in KEYS):
                 print(f"  {h} [{u}] = {v}")
 
 def src(rep):

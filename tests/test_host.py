@@ -211,3 +211,25 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"] and "model" not in line["config"]
+
+
+def test_resolve_devices_follows_datasets_device_semantics():
+    """`device` of an index config (datasets/search.py:316-347: None, int >= 0, negative = all GPUs, list = those
+    GPUs) -> (this process's GPU, sharded?) for the one-process-per-GPU engine."""
+    from viquae_b200.sharded import resolve_devices, shard_range
+    assert resolve_devices(None, 1, 0, 8) == (0, False)
+    assert resolve_devices(3, 1, 0, 8) == (3, False)
+    assert resolve_devices(None, 8, 5, 8) == (5, False)          # a replica per rank, like FAISS replicas
+    assert resolve_devices(-1, 8, 5, 8) == (5, True)
+    assert resolve_devices(-1, 1, 0, 1) == (0, False)            # a 1-GPU box: "all GPUs" is that GPU
+    assert resolve_devices([4, 6], 2, 1, 8) == (6, True)
+    assert resolve_devices([2], 1, 0, 8) == (2, False)
+    with pytest.raises(RuntimeError, match="nproc-per-node 8"):
+        resolve_devices(-1, 1, 0, 8)                             # all GPUs from one process: tell the user how to launch
+    with pytest.raises(RuntimeError, match="nproc-per-node 2"):
+        resolve_devices([0, 1], 4, 0, 8)
+    with pytest.raises(ValueError):
+        resolve_devices([0, 0], 2, 0, 8)
+    # the row ranges of the ranks tile the corpus
+    cuts = [shard_range(1_000_003, r, 8) for r in range(8)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == 1_000_003 and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))

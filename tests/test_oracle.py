@@ -35,6 +35,38 @@ def test_c_oracle_equals_numpy_oracle():
     assert np.array_equal(I, If)
 
 
+@pytest.mark.parametrize("dist", ["normal", "dpr_like", "unit"])
+def test_oracle_against_independent_referee(dist):
+    """The contraction + selection of both oracles against a referee that shares no code with them
+    (tests/dropin.py:mips_referee — scikit-learn brute-force kNN in float64 over the MIPS -> L2 augmentation): same
+    ids (no exact ties in this data: every rank-k gap is checked to exceed the fp32 accumulation error), scores
+    within 1e-5 relative — the fp32 bar `north_star` states for FAISS IndexFlatIP."""
+    from dropin import mips_referee
+    rng = np.random.default_rng(17)
+    n, d, nq, k = 20000, 96, 40, 100
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    if dist == "dpr_like":   # a common mean direction: scores cluster like real DPR scores (SURVEY §8d D2)
+        m = rng.standard_normal(d).astype(np.float32) * 0.8
+        X, Q = (m + 0.35 * X).astype(np.float32), (m + 0.35 * Q).astype(np.float32)
+    elif dist == "unit":     # CLIP / ArcFace regime
+        X, Q = flat_ip.l2norm(X), flat_ip.l2norm(Q)
+    Dr, Ir = mips_referee(Q, X, k + 1)
+    gap = (Dr[:, :-1] - Dr[:, 1:]).min()
+    Dr, Ir = Dr[:, :k], Ir[:, :k]
+    scale = np.abs(Dr).max()
+    for name, (D, I) in {"numpy": flat_ip.flat_ip_search(Q, X, k), "c": c_oracle.flat_ip(Q, X, k),
+                         "fast": flat_ip.flat_ip_search_fast(Q, X, k)}.items():
+        D, I = np.asarray(D), np.asarray(I)
+        rel = np.abs(D - Dr) / np.maximum(np.abs(Dr), 1e-30)
+        assert rel.max() <= 1e-5, (name, rel.max())
+        differ = I != Ir
+        if differ.any():  # only allowed between neighbours closer than the fp32 accumulation error
+            assert gap < 1e-5 * scale and np.abs(D - Dr)[differ].max() <= 1e-5 * scale, (name, int(differ.sum()))
+        else:
+            assert np.array_equal(I, Ir), name
+
+
 def test_c_oracle_is_fixed_order_fma():
     rng = np.random.default_rng(4)
     q = rng.standard_normal(37).astype(np.float32)

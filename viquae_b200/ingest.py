@@ -44,27 +44,34 @@ def _chunk_to_matrix(chunk):
     return flat.reshape(len(chunk), d)
 
 
-def arrow_column_blocks(dataset, column: str, max_rows: int = 262144) -> Iterator[np.ndarray]:
-    """Yields float32 [n, d] blocks covering ``dataset[column]`` in order.  Zero-copy from the Arrow chunks where
-    the column is a uniform float list; otherwise falls back to ``dataset.with_format('numpy')`` slices."""
+def arrow_column_blocks(dataset, column: str, max_rows: int = 262144, start: int = 0, stop: int = None) -> Iterator[np.ndarray]:
+    """Yields float32 [n, d] blocks covering rows ``[start, stop)`` of ``dataset[column]`` in order (the whole column
+    by default; a row shard of it for a sharded index).  Zero-copy from the Arrow chunks where the column is a uniform
+    float list; otherwise falls back to ``dataset.with_format('numpy')`` slices."""
+    n = len(dataset)
+    stop = n if stop is None else min(int(stop), n)
+    start = max(0, int(start))
     table = getattr(dataset, "data", None)
     indices = getattr(dataset, "_indices", None)
     if table is not None and indices is None and hasattr(table, "column"):
         col = table.column(column)
         ok = True
         blocks = []
+        row0 = 0
         for chunk in col.chunks:
-            m = _chunk_to_matrix(chunk)
-            if m is None:
-                ok = False
-                break
-            blocks.append(m)
+            a, b = max(start, row0), min(stop, row0 + len(chunk))
+            if b > a:
+                m = _chunk_to_matrix(chunk.slice(a - row0, b - a))
+                if m is None:
+                    ok = False
+                    break
+                blocks.append(m)
+            row0 += len(chunk)
         if ok:
             for m in blocks:
                 for i in range(0, len(m), max_rows):
                     yield m[i:i + max_rows]
             return
-    n = len(dataset)
     ds = dataset.with_format("numpy", columns=[column]) if hasattr(dataset, "with_format") else dataset
-    for i in range(0, n, max_rows):
-        yield np.asarray(ds[i:i + max_rows][column], dtype=np.float32)
+    for i in range(start, stop, max_rows):
+        yield np.asarray(ds[i:min(stop, i + max_rows)][column], dtype=np.float32)

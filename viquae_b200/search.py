@@ -66,6 +66,17 @@ class Index:
         self.do_L2norm = do_L2norm
 
 
+def _dist_world():
+    """(world_size, rank) of the default process group, (1, 0) without one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+    except Exception:
+        pass
+    return 1, 0
+
+
 def _load_from_disk(path):
     from datasets import load_from_disk
     return load_from_disk(path)
@@ -124,7 +135,10 @@ class KnowledgeBase:
         """Builds (or loads) a ``B200FlatIndex`` over ``dataset[column]`` and registers it.
 
         ``string_factory`` / ``metric_type`` / ``device`` / ``load`` / ``save_path`` mean what they mean in
-        ``add_or_load_faiss_index`` (search.py:207-249); ``dtype`` picks the storage type ("bf16" | "f16" | "f32").
+        ``add_or_load_faiss_index`` (search.py:207-249); ``dtype`` picks the storage type ("bf16" | "f16" | "f32" |
+        "f32x3").  ``device``: ``None`` or an int -> one GPU; ``-1`` (all GPUs) or a list of GPUs -> the corpus is
+        ROW-SHARDED over one process per GPU (run under ``torchrun``; the reference would replicate it,
+        datasets/search.py:329-340) and every search returns the merged result on every rank.
         Returns ``do_L2norm`` inferred from ``string_factory``."""
         for legacy in LEGACY_KEYS:
             if legacy in kwargs:
@@ -139,32 +153,42 @@ class KnowledgeBase:
         do_L2norm = parse_string_factory(string_factory, metric_type) if (column is not None or string_factory) else False
         if column is None:
             return do_L2norm
-        dev = 0 if device is None else int(device)
+        from .sharded import ShardedB200Index, resolve_devices, shard_range
+        world, rank = _dist_world()
+        dev, sharded = resolve_devices(device, world, rank, _lib.load().vq_device_count())
+        n = len(self.dataset) if self.dataset is not None else None
+        r0, r1 = shard_range(n, rank, world) if (sharded and n is not None) else (0, n)
         if load:
             path = file or save_path
             if path is None:
                 raise ValueError("load=True needs `file` (or `save_path`) pointing at a saved index")
+            if sharded:
+                path = f"{path}.shard{rank}of{world}"  # what ShardedB200Index.save wrote
             engine = B200FlatIndex.load(path, device=dev, variant=variant, dtype=dtype)
             # The file only knows what its writer knew.  With `device` set the reference strips "L2norm" from the
             # factory, pre-normalises the column and saves a plain Flat index (search.py:237-248), and normalises the
             # queries in Python because the CONFIG says "L2norm,Flat" (Index.do_L2norm, search.py:144-145): the
             # config's flag wins whenever it asks for normalisation.
             engine.do_L2norm = bool(engine.do_L2norm or do_L2norm)
+            if sharded:
+                engine = ShardedB200Index(engine)
             if self.dataset is not None and len(engine) != len(self.dataset):
                 raise ValueError(f"Index size should match Dataset size, but Index '{index_name}' at {path} has "
                                  f"{len(engine)} elements while the dataset has {len(self.dataset)} examples.")
         else:
-            n = len(self.dataset)
-            engine = B200FlatIndex(dtype=dtype, device=dev, string_factory=string_factory or "Flat", capacity=n, variant=variant)
+            engine = B200FlatIndex(dtype=dtype, device=dev, string_factory=string_factory or "Flat", capacity=r1 - r0, variant=variant,
+                                   id_offset=r0)
             if hasattr(self.dataset, "with_format"):  # HF Dataset: zero-copy Arrow chunks where possible
                 from .ingest import arrow_column_blocks
-                for block in arrow_column_blocks(self.dataset, column, max_rows=batch_size):
+                for block in arrow_column_blocks(self.dataset, column, max_rows=batch_size, start=r0, stop=r1):
                     engine.add(block)
             else:
-                for i in range(0, n, batch_size):
-                    engine.add(self._column_rows(column, i, min(n, i + batch_size)))
-            if len(engine) != n:
-                raise RuntimeError(f"ingested {len(engine)} rows of column '{column}' but the dataset has {n}")
+                for i in range(r0, r1, batch_size):
+                    engine.add(self._column_rows(column, i, min(r1, i + batch_size)))
+            if len(engine) != r1 - r0:
+                raise RuntimeError(f"ingested {len(engine)} rows of column '{column}' but rows [{r0}, {r1}) were expected")
+            if sharded:
+                engine = ShardedB200Index(engine)  # rank r holds rows [r0, r1); len(engine) is the whole corpus
             if save_path is not None:
                 engine.save(save_path)
         self._engines[index_name] = engine
@@ -360,6 +384,9 @@ def dataset_search(dataset, k=100, metric_save_path=None, map_kwargs={}, **kwarg
     searcher.qrels = Qrels(searcher.qrels)
     for name, run in searcher.runs.items():
         searcher.runs[name] = Run({q: {d: float(s) for d, s in res.items()} for q, res in run.items()}, name=name)
+    # under torchrun (row-sharded indexes) every rank holds the same runs: rank 0 alone writes the files
+    if _dist_world()[1] != 0:
+        metric_save_path = None
     if metric_save_path is not None:
         metric_save_path = Path(metric_save_path)
         metric_save_path.mkdir(exist_ok=True)
@@ -370,7 +397,8 @@ def dataset_search(dataset, k=100, metric_save_path=None, map_kwargs={}, **kwarg
         for index_name, run in searcher.runs.items():
             run.save(metric_save_path / f"{index_name}.json")
     report = {name: evaluate(searcher.qrels, run, searcher.metrics_kwargs["metrics"]) for name, run in searcher.runs.items()}
-    print(report)
+    if _dist_world()[1] == 0:
+        print(report)
     if metric_save_path is not None:
         with open(metric_save_path / "metrics.json", "wt") as file:
             json.dump(report, file)

@@ -16,6 +16,39 @@ from __future__ import annotations
 from typing import Callable, Optional, Tuple
 
 
+def resolve_devices(device, world_size: int, rank: int, n_visible: int):
+    """What ``device`` of an index config means for this process (``add_faiss_index(device=...)``,
+    datasets/search.py:316-347: ``None`` CPU, int >= 0 that GPU, negative int ALL GPUs, list those GPUs).
+
+    Returns ``(local_device, sharded)``.  The reference replicates the index over the GPUs from ONE process
+    (``index_cpu_to_all_gpus``); this engine row-shards it over one process per GPU (``torchrun``), so a multi-GPU
+    ``device`` needs an initialised process group whose size is the number of GPUs asked for:
+      * ``None`` / int >= 0 -> that one GPU (``None`` = 0, or this rank's own GPU under ``torchrun``), not sharded;
+      * ``-1`` (any negative) -> every rank's own GPU ``rank % n_visible``, sharded over the whole group;
+      * list ``[g0, g1, ...]`` -> rank r owns GPU ``g_r``; the list length must equal the group size."""
+    if device is None:
+        return (rank % max(1, n_visible) if world_size > 1 else 0), False
+    if isinstance(device, (list, tuple)):
+        devs = [int(g) for g in device]
+        if not devs or any(g < 0 for g in devs) or len(set(devs)) != len(devs):
+            raise ValueError(f"device list must hold distinct GPU ordinals >= 0, got {device!r}")
+        if len(devs) == 1:
+            return devs[0], False
+        if world_size != len(devs):
+            raise RuntimeError(f"device={devs} asks for a corpus row-sharded over {len(devs)} GPUs: launch one process per GPU "
+                               f"(python -m torch.distributed.run --nproc-per-node {len(devs)} ...); this process group has {world_size} rank(s)")
+        return devs[rank], True
+    device = int(device)
+    if device >= 0:
+        return device, False
+    if world_size == 1:
+        if n_visible > 1:
+            raise RuntimeError(f"device={device} asks for all {n_visible} GPUs: launch one process per GPU "
+                               f"(python -m torch.distributed.run --nproc-per-node {n_visible} ...) so that the corpus can be row-sharded")
+        return 0, False
+    return rank % max(1, n_visible), True
+
+
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous row range of `rank`: sizes differ by at most one row, earlier ranks take the extra."""
     base, rem = divmod(int(n_total), int(world))
@@ -172,3 +205,89 @@ class ShardedFlatIndex:
         expects from ``Dataset.search_batch`` (meerqat/ir/search.py:146)."""
         s, i = self.search_host(queries, k)
         return s.numpy(), i.numpy()
+
+
+class ShardedB200Index:
+    """What ``KnowledgeBase`` registers for ``"kind": "B200"`` with ``"device": -1`` / ``[g0, g1, ...]``: this rank's
+    row shard + the exchange, behind the same surface as ``B200FlatIndex`` (``search_batch`` -> host results on
+    EVERY rank, ``search_tensors``, ``do_L2norm``, ``device``, ``len`` = rows of the whole corpus), so that
+    ``KnowledgeBase.search_batch`` / ``Searcher`` / ``Dataset.search_batch`` run unchanged under ``torchrun``.
+    Every rank runs the same program on the same query batches (the reference's ``Dataset.map`` loop, executed
+    once per process); the collectives inside keep the ranks in step."""
+
+    def __init__(self, local_index, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.local_index = local_index
+        self.sharded = ShardedFlatIndex(local_index, group=group)
+        self.device = local_index.device
+        self.d = local_index.d
+        self.dtype = local_index.dtype
+        n = torch.tensor([local_index.ntotal], dtype=torch.int64, device=f"cuda:{self.device}")
+        dist.all_reduce(n, group=group)
+        self._ntotal = int(n.item())
+
+    @property
+    def do_L2norm(self):
+        return self.local_index.do_L2norm
+
+    @do_L2norm.setter
+    def do_L2norm(self, v):
+        self.local_index.do_L2norm = bool(v)
+
+    @property
+    def ntotal(self):
+        return self._ntotal
+
+    def __len__(self):
+        return self._ntotal
+
+    def __deepcopy__(self, memo):  # HF datasets deep-copies Dataset._indexes: the index is a handle on device memory
+        return self
+
+    def __copy__(self):
+        return self
+
+    def search_tensors(self, queries, k: int = 100, l2norm=None, out=None):
+        s, i = self.sharded.search_tensors(queries, k, l2norm=l2norm)
+        if out is not None:
+            out[0].copy_(s)
+            out[1].copy_(i)
+            return out
+        return s, i
+
+    def search_batch(self, queries, k: int = 10, **kwargs):
+        import numpy as np
+        import torch
+
+        from .index import BatchedSearchResults
+        if isinstance(queries, torch.Tensor) and queries.is_cuda:
+            return BatchedSearchResults(*self.search_tensors(queries, k))
+        queries = np.asarray(queries, dtype=np.float32)
+        if len(queries.shape) != 2:
+            raise ValueError("Shape of query must be 2D")  # datasets/search.py:380-381
+        if queries.shape[1] != self.d:
+            raise ValueError(f"dimension mismatch: index d={self.d}, queries d={queries.shape[1]}")
+        s, i = self.sharded.search_host(np.ascontiguousarray(queries), k)
+        return BatchedSearchResults(s.numpy(), i.numpy().astype(int))
+
+    def search(self, query, k: int = 10, **kwargs):
+        import numpy as np
+
+        from .index import SearchResults
+        query = np.asarray(query, dtype=np.float32)
+        if len(query.shape) != 1 and (len(query.shape) != 2 or query.shape[0] != 1):
+            raise ValueError("Shape of query is incorrect, it has to be either a 1D array or 2D (1, N)")
+        res = self.search_batch(query.reshape(1, -1), k)
+        return SearchResults(res.total_scores[0], res.total_indices[0])
+
+    def shard_file(self, file) -> str:
+        return f"{file}.shard{self.sharded.rank}of{self.sharded.world_size}"
+
+    def save(self, file, storage_options=None):
+        """Every rank writes its own shard next to ``file`` (``<file>.shard<r>of<G>`` + ``.npy``)."""
+        self.local_index.save(self.shard_file(file))
+
+    def close(self):
+        self.local_index.close()
