@@ -119,6 +119,29 @@ int vq_merge_topk(const float* scores, const int64_t* ids, int n_lists, int nq, 
 int vq_merge_topk_strided(const float* scores, const int64_t* ids, int64_t list_stride_scores, int64_t list_stride_ids, int n_lists,
                           int nq, int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream);
 
+/* ---- Cross-GPU exchange over NVLink peer memory (one process per GPU on one node), fused with the k-way merge.
+ * Stands where the reference has nothing (FAISS replicates the index per GPU, datasets/search.py:329-340) and where
+ * an ncclAllGather + vq_merge_topk pair would go.  Every rank creates a window, exports its 64-byte IPC handle,
+ * the host exchanges the handles over any side channel (the Python layer uses its process group's object all-gather) and
+ * attaches every peer.  Per search: vq_xchg_publish(packed local result) then vq_xchg_merge_topk, both asynchronous
+ * on `stream`, no host synchronisation, CUDA-graph capturable (sequence numbers live in device memory).  Collective:
+ * every rank makes the same calls in the same order. */
+typedef struct vq_xchg vq_xchg;
+#define VQ_XCHG_HANDLE_BYTES 64
+int vq_xchg_create(vq_xchg** out, int device, int rank, int world_size, size_t slot_bytes);
+int vq_xchg_export(vq_xchg* x, void* handle_out /* VQ_XCHG_HANDLE_BYTES */);
+int vq_xchg_attach(vq_xchg* x, int peer_rank, const void* handle /* VQ_XCHG_HANDLE_BYTES, from that rank's export */);
+size_t vq_xchg_slot_bytes(const vq_xchg* x);
+/* src: device pointer to this rank's contribution (packed result: scores f32 [nq, k] | pad to 8 | ids i64 [nq, k]) */
+int vq_xchg_publish(vq_xchg* x, const void* src, size_t bytes, void* stream);
+/* waits (on the device) until every rank published, pulls each query's k_in candidates of every rank straight from the
+ * peers' windows and writes the global top-k_out: out_scores f32 / out_ids i64 [nq, k_out] device pointers */
+int vq_xchg_merge_topk(vq_xchg* x, int nq, int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream);
+/* generic consumer: dst[r * bytes, (r+1) * bytes) = what rank r published (bytes % 16 == 0); used to rebuild a query batch
+ * from per-rank slices */
+int vq_xchg_gather(vq_xchg* x, size_t bytes, void* dst, void* stream);
+void vq_xchg_destroy(vq_xchg* x);
+
 /* Searcher.__call__'s per-hit post-processing (meerqat/ir/search.py:413-440) for one index and one query
  * batch: article -> passage expansion through a CSR mapping (map_offsets int64 [n_rows+1], map_targets int64
  * [nnz]; both NULL = identity), many2one (0 = overwrite like a dict, 1 = 'max'), stop after the hit that

@@ -30,6 +30,29 @@ sh = ShardedFlatIndex(local)
 sh.SLICE_EXCHANGE_MIN_QUERIES = 16          # force the all-to-all-by-query-slice exchange (64k-batch path)
 s2, i2 = sh.search_tensors(torch.from_numpy(Q).cuda(), 100)
 assert torch.equal(i2, i) and torch.equal(s2, s), "slice exchange != all-gather exchange"
+# transports: NVLink peer-memory publish + pull-merge (default) vs NCCL all-gather + merge kernel
+peer, nccl = ShardedFlatIndex(local, transport="peer"), ShardedFlatIndex(local, transport="nccl")
+Qd = torch.from_numpy(Q).cuda()
+for rep in range(5):                        # several sequence numbers: both slot parities, flags only grow
+    qs = Qd.roll(rep, 0)[: 77 - 9 * rep].contiguous()
+    sp, ip = peer.search_tensors(qs, 100)
+    sn, i_n = nccl.search_tensors(qs, 100)
+    assert peer._xchg is not None and nccl._xchg is None
+    assert torch.equal(ip, i_n) and torch.equal(sp, sn), f"peer transport != nccl transport (rep {rep})"
+assert int((ip < 0).sum()) == 0
+# host entry point: every rank uploads a slice of the queries, the slices travel through the second window
+sh_h, ih_h = peer.search_host(Q, 100)
+s_f, i_f = peer.search_tensors(Qd, 100)
+assert torch.equal(ih_h, i_f.cpu()) and torch.equal(sh_h, s_f.cpu()), "search_host (sliced upload) != search_tensors"
+only0 = peer.search_host(Q, 100, result_ranks=0)
+assert (only0 is None) == (rank != 0)
+# the whole sharded step as one CUDA graph per rank
+cap = peer.capture_search(13, 100, query_dtype=torch.float32)
+for rep in range(4):
+    cap.queries.copy_(Qd[rep:rep + 13])
+    sc, ic = cap.replay()
+    se, ie = peer.search_tensors(Qd[rep:rep + 13].contiguous(), 100)
+    assert torch.equal(ic, ie) and torch.equal(sc, se), f"graph replay {rep} != direct"
 if rank == 0:
     print("MULTI_OK")
 dist.barrier(); dist.destroy_process_group()

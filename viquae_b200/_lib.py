@@ -40,6 +40,14 @@ SIGNATURES = {
     "vq_prep_rows": (c_int, [c_void_p, c_int, c_void_p, c_int, c_uint64, c_int, c_int, c_void_p]),
     "vq_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vq_merge_topk_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vq_xchg_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_size_t]),
+    "vq_xchg_export": (c_int, [c_void_p, c_void_p]),
+    "vq_xchg_attach": (c_int, [c_void_p, c_int, c_void_p]),
+    "vq_xchg_slot_bytes": (c_size_t, [c_void_p]),
+    "vq_xchg_publish": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vq_xchg_merge_topk": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vq_xchg_gather": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "vq_xchg_destroy": (None, [c_void_p]),
     "vq_expand_hits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                        c_void_p, c_void_p]),
     "vq_fuse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

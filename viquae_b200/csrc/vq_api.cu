@@ -704,6 +704,120 @@ int vq_expand_hits(const float* scores, const int64_t* ids, int nq, int k_in, co
     return VQ_OK;
 }
 
+// ---------------------------------------------------------------- cross-GPU exchange (vq_xchg.cu)
+struct vq_xchg {
+    int device, rank, world;
+    size_t slot_bytes;
+    uint8_t* window;        // [XchgControl | slot 0 | slot 1], cudaMalloc'ed here
+    void* mapped[VQ_XCHG_MAX_RANKS];  // cudaIpcOpenMemHandle results (null for the own rank)
+    int attached;
+    vq::XchgPeers peers;
+};
+
+static size_t xchg_ctl_bytes() { return align256(sizeof(vq::XchgControl)); }
+
+int vq_xchg_create(vq_xchg** out, int device, int rank, int world_size, size_t slot_bytes) {
+    if (!out || rank < 0 || world_size < 1 || rank >= world_size || world_size > VQ_XCHG_MAX_RANKS || slot_bytes == 0)
+        return fail(VQ_ERR_INVALID, "vq_xchg_create: bad arguments (rank=%d world=%d, at most %d ranks)", rank, world_size, VQ_XCHG_MAX_RANKS);
+    VQ_ON_DEVICE(device);
+    vq_xchg* x = new vq_xchg();
+    x->device = device;
+    x->rank = rank;
+    x->world = world_size;
+    x->slot_bytes = align256(slot_bytes);
+    x->attached = 1;
+    memset(x->mapped, 0, sizeof(x->mapped));
+    memset(&x->peers, 0, sizeof(x->peers));
+    const size_t total = xchg_ctl_bytes() + 2 * x->slot_bytes;
+    cudaError_t e = cudaMalloc((void**)&x->window, total);
+    if (e == cudaSuccess) e = cudaMemset(x->window, 0, total);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (x->window) cudaFree(x->window);
+        delete x;
+        return fail(VQ_ERR_NOMEM, "vq_xchg_create: %s", cudaGetErrorString(e));
+    }
+    x->peers.ctl[rank] = (vq::XchgControl*)x->window;
+    x->peers.slots[rank] = x->window + xchg_ctl_bytes();
+    *out = x;
+    return VQ_OK;
+}
+
+int vq_xchg_export(vq_xchg* x, void* handle_out) {
+    if (!x || !handle_out) return fail(VQ_ERR_INVALID, "vq_xchg_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VQ_XCHG_HANDLE_BYTES, "IPC handle size");
+    VQ_ON_DEVICE(x->device);
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, x->window));
+    memcpy(handle_out, &h, sizeof(h));
+    return VQ_OK;
+}
+
+int vq_xchg_attach(vq_xchg* x, int peer_rank, const void* handle) {
+    if (!x || !handle || peer_rank < 0 || peer_rank >= x->world) return fail(VQ_ERR_INVALID, "vq_xchg_attach: bad arguments");
+    if (peer_rank == x->rank || x->mapped[peer_rank]) return VQ_OK;
+    VQ_ON_DEVICE(x->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->mapped[peer_rank] = p;
+    x->peers.ctl[peer_rank] = (vq::XchgControl*)p;
+    x->peers.slots[peer_rank] = (uint8_t*)p + xchg_ctl_bytes();
+    x->attached++;
+    return VQ_OK;
+}
+
+size_t vq_xchg_slot_bytes(const vq_xchg* x) { return x ? x->slot_bytes : 0; }
+
+static int xchg_ready(const vq_xchg* x, const char* who) {
+    if (!x) return fail(VQ_ERR_INVALID, "%s: null exchange", who);
+    if (x->attached != x->world) return fail(VQ_ERR_INVALID, "%s: %d of %d ranks attached", who, x->attached, x->world);
+    return VQ_OK;
+}
+
+int vq_xchg_publish(vq_xchg* x, const void* src, size_t bytes, void* stream) {
+    int rc = xchg_ready(x, "vq_xchg_publish");
+    if (rc) return rc;
+    if (!src || bytes == 0 || bytes > x->slot_bytes) return fail(VQ_ERR_INVALID, "vq_xchg_publish: %zu bytes do not fit the %zu-byte slot", bytes, x->slot_bytes);
+    VQ_ON_DEVICE(x->device);
+    rc = vq::xchg_publish_launch(x->peers.ctl[x->rank], x->peers.slots[x->rank], x->slot_bytes, src, bytes, x->peers, x->rank, x->world, (cudaStream_t)stream);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_xchg_publish: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+int vq_xchg_merge_topk(vq_xchg* x, int nq, int k_in, int k_out, float* out_scores, int64_t* out_ids, void* stream) {
+    int rc = xchg_ready(x, "vq_xchg_merge_topk");
+    if (rc) return rc;
+    if (!out_scores || !out_ids || nq < 0) return fail(VQ_ERR_INVALID, "vq_xchg_merge_topk: bad arguments");
+    VQ_ON_DEVICE(x->device);
+    rc = vq::xchg_merge_launch(x->peers.ctl[x->rank], x->peers, x->slot_bytes, x->world, nq, k_in, k_out, out_scores, (long long*)out_ids, (cudaStream_t)stream);
+    if (rc == -2) return fail(VQ_ERR_UNSUPPORTED, "vq_xchg_merge_topk: k_in=%d k_out=%d world=%d not supported", k_in, k_out, x->world);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_xchg_merge_topk: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+int vq_xchg_gather(vq_xchg* x, size_t bytes, void* dst, void* stream) {
+    int rc = xchg_ready(x, "vq_xchg_gather");
+    if (rc) return rc;
+    if (!dst || bytes == 0) return fail(VQ_ERR_INVALID, "vq_xchg_gather: bad arguments");
+    VQ_ON_DEVICE(x->device);
+    rc = vq::xchg_gather_launch(x->peers.ctl[x->rank], x->peers, x->slot_bytes, x->world, bytes, dst, (cudaStream_t)stream);
+    if (rc == -2) return fail(VQ_ERR_INVALID, "vq_xchg_gather: %zu bytes: must be a multiple of 16 and fit the slot", bytes);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_xchg_gather: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+void vq_xchg_destroy(vq_xchg* x) {
+    if (!x) return;
+    DeviceGuard guard(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; r++)
+        if (x->mapped[r]) cudaIpcCloseMemHandle(x->mapped[r]);
+    if (x->window) cudaFree(x->window);
+    delete x;
+}
+
 size_t vq_fuse_workspace_bytes(int n_runs, int nq, int k_in) {
     if (n_runs < 1 || nq < 1 || k_in < 1) return 0;
     return vq::fuse_workspace_bytes(n_runs, nq, k_in);

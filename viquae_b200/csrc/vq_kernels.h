@@ -106,6 +106,25 @@ int band_scatter_launch(const float* tmp_s, const long long* tmp_i, int nq, int 
 int merge_topk_launch(const float* scores, const long long* ids, long long stride_s, long long stride_i, int n_lists, int nq, int k_in,
                       int k_out, float* out_scores, long long* out_ids, cudaStream_t stream);
 
+// ---- cross-GPU exchange over NVLink peer memory + fused pull-merge (vq_xchg.cu)
+#define VQ_XCHG_MAX_RANKS 16
+struct XchgControl {          // head of every rank's exchange window (device memory, mapped by all peers)
+    unsigned seq;             // this rank's sequence number (local; bumped by publish)
+    unsigned done;            // CTA counter of the publish kernel in flight
+    unsigned pad[14];
+    unsigned flag[VQ_XCHG_MAX_RANKS];  // flag[r] = last sequence number rank r published (written REMOTELY by rank r)
+    unsigned pad2[16];
+};
+struct XchgPeers {            // peer-mapped pointers, indexed by rank (own rank = local pointers)
+    XchgControl* ctl[VQ_XCHG_MAX_RANKS];
+    uint8_t* slots[VQ_XCHG_MAX_RANKS];
+};
+int xchg_publish_launch(XchgControl* ctl, uint8_t* slots, size_t slot_bytes, const void* src, size_t bytes, const XchgPeers& peers, int rank,
+                        int world, cudaStream_t stream);
+int xchg_merge_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, int world, int nq, int k_in, int k_out,
+                      float* out_scores, long long* out_ids, cudaStream_t stream);
+int xchg_gather_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, int world, size_t bytes, void* dst, cudaStream_t stream);
+
 // ---- K6: run post-processing (vq_post.cu)
 int expand_hits_launch(const float* scores, const long long* ids, int nq, int k_in, const long long* map_offsets,
                        const long long* map_targets, int many2one_max, int k, int out_cap, double* out_scores, long long* out_ids,

@@ -56,11 +56,59 @@ def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+class PeerExchange:
+    """One NVLink peer-memory exchange window per rank (``vq_xchg_*``, csrc/vq_xchg.cu): the IPC handles travel once
+    through ``torch.distributed.all_gather_object``; after that ``publish`` + ``merge_topk`` / ``gather`` are plain
+    kernel launches on the caller's stream (no NCCL call, no host synchronisation, CUDA-graph capturable)."""
+
+    def __init__(self, device: int, rank: int, world_size: int, group=None, slot_bytes: int = 16 << 20):
+        import ctypes
+
+        import torch.distributed as dist
+
+        from . import _lib
+        self._lib = _lib
+        lib = _lib.load()
+        self.device, self.rank, self.world_size = device, rank, world_size
+        h = _lib.c_void_p()
+        _lib.check(lib.vq_xchg_create(ctypes.byref(h), device, rank, world_size, slot_bytes))
+        self._h = h
+        self.slot_bytes = int(lib.vq_xchg_slot_bytes(h))
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(lib.vq_xchg_export(h, buf))
+        handles = [None] * world_size
+        dist.all_gather_object(handles, bytes(buf.raw), group=group)
+        for r, raw in enumerate(handles):
+            if r != rank:
+                _lib.check(lib.vq_xchg_attach(h, r, ctypes.create_string_buffer(raw, 64)))
+        dist.barrier(group=group)  # nobody publishes before every window is mapped everywhere
+
+    def publish(self, packed, stream):
+        self._lib.check(self._lib.load().vq_xchg_publish(self._h, packed.data_ptr(), packed.numel() * packed.element_size(), stream))
+
+    def merge_topk(self, nq, k_in, k_out, out_s, out_i, stream):
+        self._lib.check(self._lib.load().vq_xchg_merge_topk(self._h, nq, k_in, k_out, out_s.data_ptr(), out_i.data_ptr(), stream))
+
+    def gather(self, nbytes, dst, stream):
+        self._lib.check(self._lib.load().vq_xchg_gather(self._h, nbytes, dst.data_ptr(), stream))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.load().vq_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedFlatIndex:
     """The local shard (a ``B200FlatIndex`` with ``id_offset`` = first global row) + the exchange step."""
 
     def __init__(self, local_index=None, *, rank: Optional[int] = None, world_size: Optional[int] = None, group=None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None, transport: str = "peer"):
         import torch.distributed as dist
 
         self.dist = dist
@@ -78,6 +126,31 @@ class ShardedFlatIndex:
             merge = merge_topk
         self._local_search = local_search
         self._merge = merge
+        # NVLink peer-memory exchange (results) and a second window for query slices; built lazily at the first search
+        # that can use them, "nccl" transport on request or when the windows cannot be mapped (not one node / no IPC)
+        import os
+        self.transport = os.environ.get("VIQUAE_B200_TRANSPORT", transport)  # "peer" (default) | "nccl"
+        self._xchg = None
+        self._xchg_q = None
+        self._xchg_failed = False
+
+    PEER_SLOT_BYTES = 16 << 20  # per-rank window slot: 8,191 queries x top-100 x 12 B fits
+
+    def _exchange(self, queries_window: bool = False):
+        """The peer-memory exchange of this index (created collectively at first use), or None for the NCCL transport."""
+        if self.transport != "peer" or self._xchg_failed or self.local_index is None:
+            return None
+        if self._xchg is None:
+            try:
+                dev = self.local_index.device
+                self._xchg = PeerExchange(dev, self.rank, self.world_size, self.group, self.PEER_SLOT_BYTES)
+                self._xchg_q = PeerExchange(dev, self.rank, self.world_size, self.group, self.PEER_SLOT_BYTES)
+            except Exception as e:  # e.g. ranks on different nodes: every rank fails the same way and uses NCCL
+                import warnings
+                warnings.warn(f"viquae_b200: NVLink peer exchange unavailable ({e}); using the NCCL all-gather transport")
+                self._xchg_failed = True
+                return None
+        return self._xchg_q if queries_window else self._xchg
 
     # above this many queries the candidates are exchanged by query slice (all-to-all), each rank merges nq/G
     # queries and the merged slices are all-gathered: G x less merge work and G x less traffic than gathering
@@ -117,11 +190,23 @@ class ShardedFlatIndex:
 
         if (self.world_size > 1 and self._packed_ok and queries.shape[0] < self.SLICE_EXCHANGE_MIN_QUERIES
                 and self.dist.get_backend(self.group) == "nccl"):
-            # scores + ids of this rank in one buffer -> ONE all-gather -> strided K4 merge
+            # scores + ids of this rank in one packed buffer
             from .index import merge_topk_packed, packed_result_buffer
             nq = queries.shape[0]
             mine, s_v, i_v = packed_result_buffer(nq, k, queries.device)
             self.local_index.search_tensors(queries, k, l2norm=l2norm, out=(s_v[0], i_v[0]))
+            xchg = self._exchange() if (k <= 128 and mine.shape[1] <= self.PEER_SLOT_BYTES) else None
+            if xchg is not None:
+                # publish into this rank's NVLink window; the merge kernel waits for every rank's flag and pulls the
+                # candidates straight from the peers' windows (exchange + merge = one kernel)
+                out_s = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+                out_i = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+                with torch.cuda.device(queries.device):
+                    stream = torch.cuda.current_stream(queries.device).cuda_stream
+                    xchg.publish(mine, stream)
+                    xchg.merge_topk(nq, k, k, out_s, out_i, stream)
+                return out_s, out_i
+            # NCCL transport: ONE all-gather of the packed buffers -> strided K4 merge
             gathered = torch.empty((self.world_size, mine.shape[1]), dtype=torch.uint8, device=queries.device)
             self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
             return merge_topk_packed(gathered, nq, k)
@@ -141,6 +226,11 @@ class ShardedFlatIndex:
             self.dist.all_gather(list(s_all.unbind(0)), s_loc.contiguous(), group=self.group)
             self.dist.all_gather(list(i_all.unbind(0)), i_loc.contiguous(), group=self.group)
         return self._merge(s_all, i_all, k)
+
+    def capture_search(self, nq: int, k: int = 100, query_dtype=None):
+        """A fixed-shape sharded search (local passes + publish + pull-merge) recorded into ONE CUDA graph per rank: the
+        latency regime at several GPUs (BASELINE config 5).  Needs the peer-memory transport (NCCL calls are not captured)."""
+        return CapturedShardedSearch(self, nq, k, query_dtype)
 
     def _transport_dtype(self):
         """dtype the queries travel in between ranks: the index's own 16-bit type (rounding is what the local search
@@ -186,7 +276,14 @@ class ShardedFlatIndex:
                     code = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
                     _lib.check(_lib.load().vq_prep_rows(mine.data_ptr(), code[mine.dtype], part.data_ptr(), code[tdt], b - a, d, int(l2),
                                                         torch.cuda.current_stream(dev).cuda_stream))
-            self.dist.all_gather_into_tensor(q_all, part, group=self.group)
+            xq = self._exchange(queries_window=True) if (part.numel() * part.element_size()) % 16 == 0 else None
+            if xq is not None and part.numel() * part.element_size() <= self.PEER_SLOT_BYTES:
+                with torch.cuda.device(dev):
+                    stream = torch.cuda.current_stream(dev).cuda_stream
+                    xq.publish(part, stream)
+                    xq.gather(part.numel() * part.element_size(), q_all, stream)
+            else:
+                self.dist.all_gather_into_tensor(q_all, part, group=self.group)
             q_all = q_all[:nq]
             sliced = True
         # a slice was normalised in fp32 BEFORE it was rounded for transport (what a single GPU does): not again
@@ -205,6 +302,56 @@ class ShardedFlatIndex:
         expects from ``Dataset.search_batch`` (meerqat/ir/search.py:146)."""
         s, i = self.search_host(queries, k)
         return s.numpy(), i.numpy()
+
+
+class CapturedShardedSearch:
+    """``ShardedFlatIndex.capture_search``: write ``queries``, ``replay()``, read ``scores`` / ``ids`` (static device
+    tensors).  Every rank must replay the same number of times (the exchange is collective)."""
+
+    def __init__(self, sharded: ShardedFlatIndex, nq: int, k: int, query_dtype=None):
+        import torch
+
+        from . import _lib
+        from .index import _tensor_dtype_code, packed_result_buffer
+        idx = sharded.local_index
+        xchg = sharded._exchange()
+        if xchg is None or k > 128:
+            raise RuntimeError("capture_search needs the NVLink peer-memory exchange (one node, k <= 128)")
+        self.sharded, self.nq, self.k = sharded, nq, k
+        dev = torch.device(f"cuda:{idx.device}")
+        self.queries = torch.zeros((nq, idx.d), dtype=query_dtype or torch.float32, device=dev)
+        self._mine, s_v, i_v = packed_result_buffer(nq, k, dev)
+        self.scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        self.ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        lib = _lib.load()
+        self._ws = torch.empty((lib.vq_index_workspace_bytes(idx._h, nq, k),), dtype=torch.uint8, device=dev)
+        l2 = int(idx.do_L2norm)
+        qcode = _tensor_dtype_code(self.queries)
+
+        def launch(stream):
+            _lib.check(lib.vq_index_search(idx._h, self.queries.data_ptr(), nq, qcode, l2, k, s_v[0].data_ptr(), i_v[0].data_ptr(),
+                                           self._ws.data_ptr(), self._ws.numel(), stream.cuda_stream))
+            xchg.publish(self._mine, stream.cuda_stream)
+            xchg.merge_topk(nq, k, k, self.scores, self.ids, stream.cuda_stream)
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                launch(side)  # warm-up outside capture (one real exchange on every rank)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                launch(torch.cuda.current_stream(dev))
+
+    def replay(self):
+        self.graph.replay()
+        return self.scores, self.ids
+
+    def __call__(self, queries):
+        self.queries.copy_(queries, non_blocking=True)
+        return self.replay()
 
 
 class ShardedB200Index:
