@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--dtype", default=None, choices=[None, "bf16", "f16", "f32", "f32x3"])
-    ap.add_argument("--variant", default=None, choices=[None, "auto", "tc_cg1", "tc_cg2", "stream"])
+    ap.add_argument("--variant", default=None, choices=[None, "auto", "tc_cg1", "tc_cg2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="configs 1 and 4: skip the secondary storage modes")
     ap.add_argument("--no-parity-check", action="store_true")
@@ -756,9 +756,11 @@ def run_fusion_config(args, ctx):
     flops = 2.0 * nq * (args.rows * 768 + 1_495_352 * 512) + 2.0 * q_face.shape[0] * 506_237 * 512
     peaks, src = load_peaks()
     peak = float(peaks.get("bf16_tflops", 1590.0))
+    fit = fusion_fit_leg(args, ctx)
     line = {
         "metric": METRIC, "value": nq / (ms / 1e3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 search, f64 fusion", "data": "synthetic",
+        "fusion_fit": fit,
         "config": {"workload": f"text {args.rows}x768 Flat + image 1495352x512 L2norm,Flat + face 506237x512 L2norm,Flat (~50% None), {nq} queries, "
                                f"top-{k} per index, article->passage expansion, defmin + gzmuv + wsum {weights}",
                    "baseline_config": "configs[2] multimodal fusion", "rows": args.rows, "nq": nq, "k": k,
@@ -776,6 +778,80 @@ def run_fusion_config(args, ctx):
         "result_sha": hashlib.sha256(fi.cpu().numpy().tobytes() + fs.cpu().numpy().tobytes()).hexdigest()[:16],
     }
     print(json.dumps(line), flush=True)
+
+
+def fusion_fit_leg(args, ctx, n_runs=4, k=100):
+    """Fusion.fit (meerqat/ir/fuse.py:193-217): the 286-point weight grid of 4 runs x nq queries x top-100, mrr@100.
+    Device: one vq_fuse_grid call (CUDA events) and the whole Fusion.fit call (wall clock, includes the dict -> dense
+    conversion on the host).  Host: the dict-based restatement (oracle/fuse_oracle.py + evaluate) on 3 of the 286
+    grid points, scaled — what ranx.optimize_fusion does per grid point in the reference."""
+    import numpy as np
+    import torch
+    from viquae_b200 import _lib, fuse, runs
+
+    nq = args.nq
+    rng = np.random.default_rng(5)
+    run_dicts = []
+    for r in range(n_runs):
+        mu, sd = [(71.3, 2.2), (0.3, 0.1), (0.25, 0.08), (20.0, 5.0)][r % 4]
+        run = {}
+        for q in range(nq):
+            docs = rng.choice(2000, size=k, replace=False) + 2000 * (q % 50)
+            run[f"q{q}"] = {str(int(d)): float(v) for d, v in zip(docs, np.sort(rng.normal(mu, sd, k))[::-1])}
+        run_dicts.append(run)
+    qrels = runs.Qrels({f"q{q}": {d: 1 for d in list(run_dicts[q % n_runs][f"q{q}"])[3:40:12]} for q in range(nq)})
+    f = fuse.Fusion(qrels=qrels, runs=[fuse.Run(r) for r in run_dicts], norm="zmuv", defmin=True, device=ctx.local_rank)
+    f.fit("mrr@100")  # warm-up (module load, allocator)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = f.fit("mrr@100")
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    (params, score), = res.values()
+    # device-only: the same call on resident arrays, CUDA events
+    dense = fuse.DenseRuns(f.runs)
+    dev = ctx.device
+    d_s, d_i = torch.from_numpy(dense.scores).to(dev), torch.from_numpy(dense.ids).to(dev)
+    grid = list(fuse.weight_grid(n_runs))
+    d_w = torch.tensor(grid, dtype=torch.float64, device=dev)
+    rel = np.full((nq, 4), -1, dtype=np.int64)
+    for qi, q in enumerate(dense.q_ids):
+        c = [dense._encode[d] for d in qrels.qrels[q]]
+        rel[qi, :len(c)] = c
+    d_rel = torch.from_numpy(rel).to(dev)
+    d_n = torch.full((nq,), 4, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    R, _, k_in = dense.scores.shape
+    ws = torch.empty(lib.vq_fuse_grid_workspace_bytes(R, nq, k_in, len(grid)) + 256, dtype=torch.uint8, device=dev)
+    out_m = torch.empty((len(grid),), dtype=torch.float64, device=dev)
+    out_b = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def call():
+        _lib.check(lib.vq_fuse_grid(d_s.data_ptr(), d_i.data_ptr(), R, nq, k_in, 1, 1, d_w.data_ptr(), len(grid), d_rel.data_ptr(), 4, d_n.data_ptr(), nq,
+                                    0, 100, out_m.data_ptr(), out_b.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    for _ in range(3):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / 10
+    out = {"what": f"Fusion.fit('mrr@100'), {n_runs} runs x {nq} queries x top-{k}, {len(grid)} weight vectors, zmuv + defmin",
+           "device_grid_ms": dev_ms, "fit_call_wall_ms": wall_ms, "best_weights": params["weights"], "best_score": score,
+           "device_equals_fit": bool(abs(float(out_m[int(out_b.item())].item()) - score) < 1e-12)}
+    if not args.no_cpu_baseline:
+        from oracle import fuse_oracle
+        sample = [grid[0], grid[len(grid) // 2], grid[-1]]
+        t0 = time.perf_counter()
+        host_scores = [runs.evaluate(qrels, runs.Run(fuse_oracle.fuse(run_dicts, w, norm="zmuv", defmin=True)), "mrr@100") for w in sample]
+        host_s = (time.perf_counter() - t0) / len(sample) * len(grid)
+        idx = [0, len(grid) // 2, len(grid) - 1]
+        got = out_m.cpu().numpy()[idx]
+        out["host_dict_restatement_ms"] = host_s * 1e3
+        out["host_sample"] = f"{len(sample)} of {len(grid)} grid points timed, scaled; same scores: {bool(np.allclose(got, host_scores, atol=1e-12))}"
+    return out
 
 
 def run_ours(args):

@@ -43,7 +43,6 @@ extern "C" {
 #define VQ_VARIANT_AUTO 0
 #define VQ_VARIANT_TC_CG1 1   /* tcgen05 128x256 tiles, one CTA per SM */
 #define VQ_VARIANT_TC_CG2 2   /* tcgen05 cta_group::2, 256x256 tiles per CTA pair */
-#define VQ_VARIANT_STREAM 3   /* small-batch HBM-streaming kernel */
 
 typedef struct vq_index vq_index;
 
@@ -162,6 +161,32 @@ size_t vq_fuse_workspace_bytes(int n_runs, int nq, int k_in);
 int vq_fuse(const double* scores, const int64_t* ids, const double* weights, int n_runs, int nq, int k_in, int defmin,
             int norm, double* out_scores, int64_t* out_ids, int32_t* out_counts, void* workspace, size_t workspace_bytes,
             void* stream);
+
+/* Fusion.fit (meerqat/ir/fuse.py:193-217 -> ranx.optimize_fusion): the grid search over weight vectors as one
+ * device pass.  Same inputs as vq_fuse plus weights float64 [n_weights, n_runs] (the reference's grid: step 0.1,
+ * summing to 1), the relevant documents of every query rel int64 [nq, max_rel] (doc ids, < 0 = padding; at most 256
+ * of them can lie in a query's union), n_rel_total int32 [nq] (relevant documents in the qrels, retrieved or not:
+ * recall's denominator) and n_judged (queries in the qrels: the mean's denominator, like ranx).  metric: 0 mrr,
+ * 1 precision, 2 hit_rate, 3 recall, each @cut (cut = 0: no cut).  Union + default-minimum + normalisation happen
+ * once; per weight vector only the RANKS of the relevant documents are computed (a counting pass, no sort).
+ * Outputs: out_metric float64 [n_weights], out_best int32 [1] = index of the first best weight vector. */
+size_t vq_fuse_grid_workspace_bytes(int n_runs, int nq, int k_in, int n_weights);
+int vq_fuse_grid(const double* scores, const int64_t* ids, int n_runs, int nq, int k_in, int defmin, int norm, const double* weights,
+                 int n_weights, const int64_t* rel, int max_rel, const int32_t* n_rel_total, int n_judged, int metric, int cut,
+                 double* out_metric, int32_t* out_best, void* workspace, size_t workspace_bytes, void* stream);
+
+/* In-batch similarity of the bi-encoder's evaluation step (meerqat/train/trainee.py:454-458 + train/metrics.py:22-37),
+ * forward only: similarities = Q . C^T (fp32 accumulation), log_softmax over each row, NLL of the labelled context and
+ * its 1-based rank in the row (ties: lower index first).  Device pointers.  q [n_q, d], c [n_c, d] of `dtype`; labels
+ * int64 [n_q] (ignore_index or out-of-range = ignored: nll 0, rank 0); log_probs float32 [n_q, n_c] or NULL;
+ * nll float32 [n_q]; rank int32 [n_q].  The caller averages nll over the non-ignored rows (the NLL loss's 'mean' reduction). */
+int vq_inbatch_logprobs(const void* q, const void* c, int dtype, int n_q, int n_c, int d, const int64_t* labels, int64_t ignore_index,
+                        float* log_probs, float* nll, int32_t* rank, void* stream);
+
+/* Hard-negative mining after a search (EXPERIMENTS.rst:78-103: retrieved ids split into relevant ones and
+ * `search_irrelevant_indices`): is_relevant[q, j] = 1 iff ids[q, j] is in the query's ASCENDING relevant-id list
+ * rel_ids[rel_offsets[q] .. rel_offsets[q+1]).  Device pointers; ids int64 [nq, k] as returned by vq_index_search. */
+int vq_mark_relevant(const int64_t* ids, int nq, int k, const int64_t* rel_offsets, const int64_t* rel_ids, uint8_t* is_relevant, void* stream);
 
 #ifdef __cplusplus
 }

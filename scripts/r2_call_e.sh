@@ -1,0 +1,20 @@
+#!/bin/bash
+# round-2 GPU call E (1 GPU): full GPU suite, latency-regime A/B (pass schedule, round-1 tc kernel) on one box
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/e_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/e_pytest.log
+for rows in 1500000 12000000; do
+  timeout 600 python bench.py --config 5 --rows $rows --steps 500 > gpurun_out/e_c5_${rows}_auto.json 2>> gpurun_out/e.err
+  VQ_PASS_RATIO=8 timeout 600 python bench.py --config 5 --rows $rows --steps 500 > gpurun_out/e_c5_${rows}_ratio8.json 2>> gpurun_out/e.err
+  VQ_PASS_RATIO=8 VIQUAE_B200_LIB=$PWD/viquae_b200/libviquae_b200_prev.so timeout 600 python bench.py --config 5 --rows $rows --steps 500 > gpurun_out/e_c5_${rows}_prevtc.json 2>> gpurun_out/e.err
+done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/e_launches_nq1_shard.csv python bench.py --config 5 --rows 1500000 --steps 2 --warmup 1 --nq 1 > /dev/null 2>> gpurun_out/e.err
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/e_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, [ (r['nq'], r['p50_us'], r['p99_us']) for r in d['latency']['per_batch_size']])
+    except Exception as e:
+        print(f, 'ERR', e)
+PY
+tail -n 5 gpurun_out/e.err

@@ -95,3 +95,49 @@ def test_fit_dense_metric_equals_host_metric(golden_dir):
     assert abs(host - score) < 1e-12
     best_host = max(runs.evaluate(qrels, f._fused(w, "zmuv"), "mrr@100") for w in fuse.weight_grid(3))
     assert abs(best_host - score) < 1e-12
+
+
+@pytest.mark.parametrize("norm", ["zmuv", "gzmuv", "min-max", None])
+def test_grid_search_kernel_equals_host_evaluation_at_every_grid_point(golden_dir, norm):
+    """vq_fuse_grid (ranks of the relevant documents by counting, no sort) vs the dict-based evaluate() of the run
+    that vq_fuse produces for the same weights — for every point of the 66-point grid and every metric the reference
+    reports (search.py:397), with a judged query that no run answers and a relevant document nobody retrieved."""
+    from viquae_b200 import fuse, runs
+    g = json.load(open(os.path.join(golden_dir, "fusion_golden.json")))
+    rr = [fuse.Run(r) for r in g["runs"]]
+    q = {qid: {d: 1 for d in list(res)[1:6:2]} for qid, res in g["runs"][0].items()}
+    q["q1"]["never-retrieved"] = 1
+    q["q2"] = {d: 0 for d in q["q2"]}            # judged, nothing relevant
+    q["not-in-any-run"] = {"5": 1}
+    qrels = runs.Qrels(q)
+    f = fuse.Fusion(qrels=qrels, runs=rr, norm=norm, defmin=True)
+    for metric in ("mrr@100", "precision@1", "precision@5", "hit_rate@3", "recall@10", "mrr@2"):
+        res = f.fit(metric)
+        (params, score), = res.values()
+        report = f.grid_reports[(norm, "wsum")]
+        assert len(report) == 66
+        host = [runs.evaluate(qrels, f._fused(w, norm), metric) for w, _ in report]
+        dev = [v for _, v in report]
+        assert np.allclose(dev, host, rtol=0, atol=1e-12), (metric, np.abs(np.array(dev) - np.array(host)).max())
+        first_best = int(np.argmax(np.array(host) > max(host) - 1e-15))
+        assert params["weights"] == [round(w, 10) for w in report[first_best][0]] and abs(score - host[first_best]) < 1e-12
+
+
+def test_fusion_beyond_the_old_2048_entry_limit():
+    """n_runs * k_in above 2048 (a hit on a long article expands to hundreds of passages): served from dynamic
+    shared memory up to 16384 entries, equal to the oracle."""
+    from oracle import fuse_oracle
+    from viquae_b200 import fuse
+    rng = np.random.default_rng(8)
+    runs_ = []
+    for r in range(3):
+        run = {}
+        for qi in range(5):
+            docs = rng.choice(4000, size=900, replace=False)
+            run[f"q{qi}"] = {str(int(d)): float(s) for d, s in zip(docs, np.sort(rng.normal(0, 1, 900))[::-1])}
+        runs_.append(run)
+    fused = fuse.Fusion(qrels=None, runs=[fuse.Run(r) for r in runs_], norm="zmuv", defmin=True).test({"weights": [0.5, 0.3, 0.2]}, metrics=[])
+    ref = fuse_oracle.fuse(runs_, [0.5, 0.3, 0.2], norm="zmuv", defmin=True)
+    for qid in ref:
+        assert set(fused.run[qid]) == set(ref[qid])
+        assert np.allclose([fused.run[qid][d] for d in ref[qid]], list(ref[qid].values()), rtol=1e-9, atol=1e-9)

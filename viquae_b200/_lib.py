@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("VIQUAE_B200_LIB") or os.path.join(_HERE, "libviquae_b
 
 F32, BF16, F16 = 0, 1, 2
 F32X3 = 3  # storage only: fp32 values split into three bf16 terms, tensor-core contraction at fp32 fidelity
-VARIANT_AUTO, VARIANT_TC_CG1, VARIANT_TC_CG2, VARIANT_STREAM = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_TC_CG1, VARIANT_TC_CG2 = 0, 1, 2
 ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4
 
 # every symbol include/viquae_b200.h declares: name -> (restype, argtypes)
@@ -53,6 +53,11 @@ SIGNATURES = {
     "vq_fuse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vq_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                         c_void_p, c_size_t, c_void_p]),
+    "vq_inbatch_logprobs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vq_mark_relevant": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vq_fuse_grid_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "vq_fuse_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

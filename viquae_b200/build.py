@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(HERE, "libviquae_b200.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
-SOURCES = ["vq_api.cu", "vq_prep.cu", "vq_fp32.cu", "vq_stream.cu", "vq_tc.cu", "vq_merge.cu", "vq_fuse.cu", "vq_post.cu", "vq_xchg.cu"]
+SOURCES = ["vq_api.cu", "vq_prep.cu", "vq_fp32.cu", "vq_tc.cu", "vq_merge.cu", "vq_fuse.cu", "vq_post.cu", "vq_xchg.cu", "vq_inbatch.cu"]
 HEADERS = ["vq_common.cuh", "vq_kernels.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -231,7 +231,7 @@ int vq_index_set_id_offset(vq_index* idx, int64_t off) {
     return VQ_OK;
 }
 int vq_index_set_variant(vq_index* idx, int variant) {
-    if (!idx || variant < 0 || variant > 3) return fail(VQ_ERR_INVALID, "vq_index_set_variant: bad variant %d", variant);
+    if (!idx || variant < 0 || variant > 2) return fail(VQ_ERR_INVALID, "vq_index_set_variant: bad variant %d", variant);
     idx->variant = variant;
     return VQ_OK;
 }
@@ -387,7 +387,7 @@ int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* ds
 // ---- variant choice + workspace carving shared by workspace_bytes() and search()
 #define VQ_MAX_PASSES 6
 struct SearchPlan {
-    int kind;  // 0 = fp32 SIMT, 1 = tensor core, 2 = stream
+    int kind;  // 0 = fp32 SIMT, 1 = tensor core
     // tensor-core path: corpus tiles [tile_b[p], tile_b[p+1]) are searched by pass p with thresholds primed
     // from all earlier passes (see make_plan)
     int n_passes;
@@ -396,7 +396,6 @@ struct SearchPlan {
     int ratio;
     vq::TcPlan tc[VQ_MAX_PASSES];
     vq::F32Plan f32[VQ_MAX_PASSES];
-    vq::StreamPlan st;
     int pass_sets;  // largest number of candidate-list sets any pass writes (set 0 is the running merge)
     int nq_pad;
     size_t off_q, off_lists, off_counts, off_thr, off_prog, total;
@@ -454,13 +453,7 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     } else {
         int variant = idx->variant;
         if (variant == VQ_VARIANT_AUTO) variant = (nq <= 128) ? VQ_VARIANT_TC_CG1 : VQ_VARIANT_TC_CG2;
-        if (variant == VQ_VARIANT_STREAM && (nq > 32 || idx->dtype == VQ_F32X3)) variant = VQ_VARIANT_TC_CG1;
-        if (variant == VQ_VARIANT_STREAM) {
-            sp->kind = 2;
-            vq::stream_plan(nq, n, idx->n_sms, &sp->st);
-            sp->pass_sets = sp->st.n_chunks;
-            sp->nq_pad = sp->st.nq_pad;
-        } else {
+        {
             sp->kind = 1;
             const int cg = variant == VQ_VARIANT_TC_CG2 ? 2 : 1;
             // Threshold priming.  A query's k-th best score over ANY subset of the corpus is a lower bound of its
@@ -479,11 +472,14 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
                 env_first = a ? atoi(a) : 0;
                 env_ratio = b2 ? atoi(b2) : 0;
             }
-            const int ratio = env_ratio > 1 ? env_ratio : 8;  // measured: 6..8 beats 16 by 2-4 % (lighter last pass, one more small pass)
+            int ratio = env_ratio > 1 ? env_ratio : 8;  // measured: 6..8 beats 16 by 2-4 % (lighter last pass, one more small pass)
             int first = (idx->n_sms / cg) / m_tiles;
             if (first < 1) first = 1;
             if (first > 28) first = 28;  // every row of the first pass becomes a candidate: keep its merge one 8192-key sort
             if (env_first > 0) first = env_first;
+            // (Fewer, larger passes for HBM-bound batches were measured and lose: a pass boundary costs ~30 us of fixed
+            // latency, but the one-CTA-per-query merge of a 7,000-row unprimed pass costs 51 us and a CTA-wide shared-memory
+            // sort is slower still — profiles/README.md, "latency regime".  Ratio 8 stays the schedule for every batch size.)
             sp->ratio = ratio;
             const int np = pass_schedule(n_tiles, first, ratio, sp->tile_b, sp->stride);
             sp->n_passes = np;
@@ -544,7 +540,7 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
             vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, 1, ub_score, ub_row};
             rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->kd, idx->kdtype, k, sp.tc[p], pass, lists, counts, progress, s);
             // first pass: every row is a candidate; primed passes add ~ratio * k candidates per query
-            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : 4096;
+            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : ((sp.ratio + 2) * k > 2048 ? (sp.ratio + 2) * k : 2048);  // ~ (ratio + 1) * k; more takes gather rounds
             if (!rc)
                 rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.tc[p].list_sets, sp.nq_pad, nq, k, id_offset, last ? nullptr : thr,
                                             last ? out_scores : nullptr, last ? out_ids : nullptr, expected, s);
@@ -556,20 +552,12 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
             rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, ntot, idx->ld, idx->d, k, sp.f32[p],
                                      sp.tile_b[p], sp.tile_b[p + 1], sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, ub_score, ub_row,
                                      lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
-            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 128 + k : 4096;
+            const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 128 + k : 2048;
             if (!rc)
                 rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.f32[p].n_chunks, sp.nq_pad, nq, k, id_offset, last ? nullptr : thr,
                                             last ? out_scores : nullptr, last ? out_ids : nullptr, expected, s);
             idx->launches += 2;
         }
-    } else {
-        if (ub_score) return -3;  // the streaming kernel has no banded mode
-        rc = vq::stream_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->kd, idx->kdtype, k, sp.st,
-                                    lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
-        if (!rc)
-            rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, id_offset, nullptr, out_scores, out_ids,
-                                        sp.pass_sets * k, s);
-        idx->launches += 2;
     }
     return rc;
 }
@@ -586,7 +574,6 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     VQ_ON_DEVICE(idx->device);
     SearchPlan sp;
     make_plan(idx, nq, &sp);
-    if (k > VQ_KMAX && sp.kind == 2) return fail(VQ_ERR_UNSUPPORTED, "vq_index_search: the streaming variant serves k <= %d", VQ_KMAX);
     const size_t need = sp.total + (k > VQ_KMAX ? band_bytes(nq, sp.nq_pad) : 0);
     if (workspace_bytes < need) return fail(VQ_ERR_NOMEM, "vq_index_search: workspace %zu < %zu bytes", workspace_bytes, need);
     uint8_t* ws = (uint8_t*)workspace;
@@ -836,9 +823,51 @@ int vq_fuse(const double* scores, const int64_t* ids, const double* weights, int
     fp.norm = norm;
     int rc = vq::fuse_launch(scores, (const long long*)ids, weights, fp, out_scores, (long long*)out_ids, out_counts, workspace,
                              workspace_bytes, (cudaStream_t)stream);
-    if (rc == -3) return fail(VQ_ERR_UNSUPPORTED, "vq_fuse: n_runs=%d k_in=%d norm=%d outside the supported range (n_runs*k_in <= 2048, n_runs <= 16)", n_runs, k_in, norm);
+    if (rc == -3) return fail(VQ_ERR_UNSUPPORTED, "vq_fuse: n_runs=%d k_in=%d norm=%d outside the supported range (n_runs*k_in <= 16384, n_runs <= 16)", n_runs, k_in, norm);
     if (rc == -4) return fail(VQ_ERR_NOMEM, "vq_fuse: workspace too small");
     if (rc) return fail(VQ_ERR_CUDA, "vq_fuse: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+int vq_inbatch_logprobs(const void* q, const void* c, int dtype, int n_q, int n_c, int d, const int64_t* labels, int64_t ignore_index,
+                        float* log_probs, float* nll, int32_t* rank, void* stream) {
+    if (!q || !c || !labels || !nll || !rank || n_q < 0 || n_c < 1 || d < 1 || !dtype_ok(dtype))
+        return fail(VQ_ERR_INVALID, "vq_inbatch_logprobs: bad arguments");
+    int rc = vq::inbatch_launch(q, c, dtype, n_q, n_c, d, (const long long*)labels, (long long)ignore_index, log_probs, nll, rank, (cudaStream_t)stream);
+    if (rc == -2) return fail(VQ_ERR_UNSUPPORTED, "vq_inbatch_logprobs: d + n_c = %d floats exceed the shared memory of one CTA", d + n_c);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_inbatch_logprobs: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+int vq_mark_relevant(const int64_t* ids, int nq, int k, const int64_t* rel_offsets, const int64_t* rel_ids, uint8_t* is_relevant, void* stream) {
+    if (!ids || !rel_offsets || !is_relevant || nq < 0 || k < 1) return fail(VQ_ERR_INVALID, "vq_mark_relevant: bad arguments");
+    int rc = vq::mark_relevant_launch((const long long*)ids, nq, k, (const long long*)rel_offsets, (const long long*)rel_ids, is_relevant, (cudaStream_t)stream);
+    if (rc) return fail(VQ_ERR_CUDA, "vq_mark_relevant: launch failed (%d)", rc);
+    return VQ_OK;
+}
+
+size_t vq_fuse_grid_workspace_bytes(int n_runs, int nq, int k_in, int n_weights) {
+    if (n_runs < 1 || nq < 1 || k_in < 1 || n_weights < 1) return 0;
+    return vq::fuse_grid_workspace_bytes(n_runs, nq, k_in, n_weights);
+}
+
+int vq_fuse_grid(const double* scores, const int64_t* ids, int n_runs, int nq, int k_in, int defmin, int norm, const double* weights,
+                 int n_weights, const int64_t* rel, int max_rel, const int32_t* n_rel_total, int n_judged, int metric, int cut,
+                 double* out_metric, int32_t* out_best, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!scores || !ids || !weights || !rel || !n_rel_total || !out_metric || !out_best || !workspace)
+        return fail(VQ_ERR_INVALID, "vq_fuse_grid: null pointer");
+    vq::FuseParams fp;
+    fp.n_runs = n_runs;
+    fp.nq = nq;
+    fp.k_in = k_in;
+    fp.u_max = n_runs * k_in;
+    fp.defmin = defmin;
+    fp.norm = norm;
+    int rc = vq::fuse_grid_launch(scores, (const long long*)ids, fp, weights, n_weights, (const long long*)rel, max_rel, n_rel_total, n_judged, metric,
+                                  cut, out_metric, out_best, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc == -3) return fail(VQ_ERR_UNSUPPORTED, "vq_fuse_grid: n_runs=%d k_in=%d norm=%d metric=%d outside the supported range", n_runs, k_in, norm, metric);
+    if (rc == -4) return fail(VQ_ERR_NOMEM, "vq_fuse_grid: workspace too small");
+    if (rc) return fail(VQ_ERR_CUDA, "vq_fuse_grid: launch failed (%d)", rc);
     return VQ_OK;
 }
 

@@ -46,7 +46,8 @@ f32_topk_kernel(const float* __restrict__ Q, int nq, int ld_q, const float* __re
         uint64_t* item_lists = lists + ((size_t)chunk * nq_pad + q0) * VQ_CAP;
         if (tid < BM) {
             cnt_s[tid] = 0;
-            // primed threshold (k-th score of the rows of earlier passes, all with lower ids) or -FLT_MAX
+            // primed threshold (next float below the k-th score of the strided samples the earlier passes searched: those
+            // rows may have HIGHER ids, so an equal score must still pass the strict compare) or -FLT_MAX
             thr_s[tid] = (q0 + tid < nq) ? (init_thr ? init_thr[q0 + tid] : -FLT_MAX) : INFINITY;
             ubs_s[tid] = (ub_score && q0 + tid < nq) ? ub_score[q0 + tid] : INFINITY;
             ubr_s[tid] = (ub_row && q0 + tid < nq) ? ub_row[q0 + tid] : 0u;

@@ -22,7 +22,7 @@ namespace vq {
 namespace fuse {
 
 constexpr int THREADS = 256;
-constexpr int E_MAX = 2048;   // n_runs * k_in entries per query (48 KB static smem budget)
+constexpr int E_MAX = 16384;  // n_runs * k_in entries per query: keys (8 B) + ids (4 B) per entry in dynamic shared memory
 constexpr int R_MAX = 16;
 
 __device__ __forceinline__ void sort_desc_u64(uint64_t* keys, int S) {
@@ -103,7 +103,7 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 __global__ void __launch_bounds__(THREADS)
 union_kernel(const double* __restrict__ scores, const long long* __restrict__ ids, int R, int nq, int k_in, int defmin,
              double* __restrict__ mat, long long* __restrict__ doc, int* __restrict__ ucount) {
-    __shared__ uint64_t keys[E_MAX];
+    extern __shared__ uint64_t keys[];  // [pow2_ge(R * k_in)]
     __shared__ double red[THREADS];
     __shared__ int scan[THREADS];
     __shared__ double run_min[R_MAX];
@@ -232,18 +232,9 @@ __global__ void gstats_final_kernel(const double* __restrict__ partial, int n_bl
     gstats[2 * r + 1] = n > 0.0 ? sqrt(m2 / n) : 0.0;
 }
 
-// ---- C: normalise + weighted sum + sort
-__global__ void __launch_bounds__(THREADS)
-combine_kernel(const double* __restrict__ mat, const long long* __restrict__ doc, const int* __restrict__ ucount,
-               const double* __restrict__ weights, const double* __restrict__ gstats, int R, int nq, int E, int norm,
-               double* __restrict__ out_scores, long long* __restrict__ out_ids, int* __restrict__ out_counts) {
-    __shared__ uint64_t keys[E_MAX];
-    __shared__ uint32_t vals[E_MAX];
-    __shared__ double red[THREADS];
-    __shared__ double sub[R_MAX], div[R_MAX];
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const int U = ucount[q];
-    const double* m = mat + (size_t)q * E * R;
+// per-run normalisation constants of one query: s' = (s - sub[r]) / div[r].  Called by all threads of the CTA.
+__device__ __forceinline__ void norm_stats(const double* m, int U, int R, int norm, const double* gstats, double* red, double* sub, double* div) {
+    const int tid = threadIdx.x;
     for (int r = 0; r < R; r++) {
         double a = 0.0, b = 1.0;
         if (norm == 1) {  // zmuv over this query's entries of run r
@@ -271,6 +262,21 @@ combine_kernel(const double* __restrict__ mat, const long long* __restrict__ doc
         if (tid == 0) { sub[r] = a; div[r] = b; }
     }
     __syncthreads();
+}
+
+// ---- C: normalise + weighted sum + sort
+__global__ void __launch_bounds__(THREADS)
+combine_kernel(const double* __restrict__ mat, const long long* __restrict__ doc, const int* __restrict__ ucount,
+               const double* __restrict__ weights, const double* __restrict__ gstats, int R, int nq, int E, int norm,
+               double* __restrict__ out_scores, long long* __restrict__ out_ids, int* __restrict__ out_counts) {
+    extern __shared__ uint64_t keys[];  // [S_max] fused-score keys, then [S_max] doc ids (uint32)
+    __shared__ double red[THREADS];
+    __shared__ double sub[R_MAX], div[R_MAX];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int U = ucount[q];
+    uint32_t* vals = reinterpret_cast<uint32_t*>(keys + pow2_ge(E));
+    const double* m = mat + (size_t)q * E * R;
+    norm_stats(m, U, R, norm, gstats, red, sub, div);
     const int S = pow2_ge(U);
     for (int u = tid; u < S; u += THREADS) {
         uint64_t key = 0ull;
@@ -303,9 +309,152 @@ combine_kernel(const double* __restrict__ mat, const long long* __restrict__ doc
     if (tid == 0) out_counts[q] = U;
 }
 
+
+// ---- D: grid search over weight vectors (Fusion.fit, meerqat/ir/fuse.py:193-217 -> ranx.optimize_fusion).
+// D1 normalises the filled matrix once per query (the statistics do not depend on the weights) and locates the
+// query's relevant documents in its union.  D2 evaluates every weight vector: the metrics the reference optimises
+// (mrr@k, precision@k, hit_rate@k, recall@k) only need the RANKS of the relevant documents, and
+//     rank(d) = 1 + #{u : fused(u) > fused(d)  or  (fused(u) == fused(d) and id(u) < id(d))}
+// is a counting pass over the union — no sort per weight vector.  D3 averages over the judged queries in a fixed
+// order and picks the first best weight vector.
+constexpr int REL_MAX = 256;  // relevant documents of one query that can appear in its union
+
+__global__ void __launch_bounds__(THREADS)
+grid_prepare_kernel(double* __restrict__ mat, const long long* __restrict__ doc, const int* __restrict__ ucount, const double* __restrict__ gstats,
+                    int R, int nq, int E, int norm, const long long* __restrict__ rel, int max_rel, int* __restrict__ rel_pos,
+                    int* __restrict__ rel_cnt) {
+    __shared__ double red[THREADS];
+    __shared__ double sub[R_MAX], div[R_MAX];
+    __shared__ int n_found;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int U = ucount[q];
+    double* m = mat + (size_t)q * E * R;
+    norm_stats(m, U, R, norm, gstats, red, sub, div);
+    for (int i = tid; i < U * R; i += THREADS) {
+        const double v = m[i];
+        if (!isnan(v)) m[i] = (v - sub[i % R]) / div[i % R];
+    }
+    // relevant documents present in the union: doc[q][0..U) ascends by id -> binary search
+    if (tid == 0) n_found = 0;
+    __syncthreads();
+    const long long* dq = doc + (size_t)q * E;
+    for (int j = tid; j < max_rel; j += THREADS) {
+        const long long want = rel[(size_t)q * max_rel + j];
+        if (want < 0) continue;
+        int lo = 0, hi = U;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (dq[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        if (lo < U && dq[lo] == want) {
+            const int at = atomicAdd(&n_found, 1);
+            if (at < REL_MAX) rel_pos[(size_t)q * REL_MAX + at] = lo;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) rel_cnt[q] = n_found < REL_MAX ? n_found : REL_MAX;
+}
+
+// grid (nq, ceil(W / warps)): one warp per weight vector
+__global__ void __launch_bounds__(THREADS)
+grid_eval_kernel(const double* __restrict__ matn, const long long* __restrict__ doc, const int* __restrict__ ucount,
+                 const double* __restrict__ weights, int W, int R, int nq, int E, const int* __restrict__ rel_pos, const int* __restrict__ rel_cnt,
+                 const int* __restrict__ n_rel_total, int metric, int cut, double* __restrict__ per_query) {
+    const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.y * (THREADS / 32) + warp;
+    if (w >= W) return;
+    const int U = ucount[q], nrel = rel_cnt[q];
+    const double* m = matn + (size_t)q * E * R;
+    const long long* dq = doc + (size_t)q * E;
+    double wt[R_MAX];
+#pragma unroll
+    for (int r = 0; r < R_MAX; r++) wt[r] = r < R ? weights[(size_t)w * R + r] : 0.0;
+    const int kk = cut > 0 ? cut : 0x7fffffff;
+    int hits = 0, best_rank = 0x7fffffff;
+    for (int j0 = 0; j0 < nrel; j0 += 8) {  // eight relevant documents per sweep over the union
+        double fd[8];
+        long long idd[8];
+        int cnt[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            cnt[j] = 0;
+            fd[j] = 0.0;
+            idd[j] = -1;
+            if (j0 + j < nrel) {
+                const int u = rel_pos[(size_t)q * REL_MAX + j0 + j];
+                double f = 0.0;
+#pragma unroll
+                for (int r = 0; r < R_MAX; r++)
+                    if (r < R) { const double v = m[(size_t)u * R + r]; if (!isnan(v)) f += wt[r] * v; }
+                fd[j] = f;
+                idd[j] = dq[u];
+            }
+        }
+        for (int u = lane; u < U; u += 32) {
+            double f = 0.0;
+#pragma unroll
+            for (int r = 0; r < R_MAX; r++)
+                if (r < R) { const double v = m[(size_t)u * R + r]; if (!isnan(v)) f += wt[r] * v; }
+            const long long id = dq[u];
+#pragma unroll
+            for (int j = 0; j < 8; j++) cnt[j] += (f > fd[j] || (f == fd[j] && id < idd[j])) ? 1 : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int c = cnt[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(VQ_FULL_MASK, c, o);
+            if (j0 + j < nrel) {
+                const int rank = c + 1;
+                if (rank <= kk) hits++;
+                best_rank = rank < best_rank ? rank : best_rank;
+            }
+        }
+    }
+    if (lane == 0) {
+        double v = 0.0;
+        if (metric == 0) v = best_rank <= kk ? 1.0 / (double)best_rank : 0.0;                       // mrr@k
+        else if (metric == 1) v = (double)hits / (double)(cut > 0 ? cut : (U > 0 ? U : 1));        // precision@k
+        else if (metric == 2) v = hits > 0 ? 1.0 : 0.0;                                             // hit_rate@k
+        else v = n_rel_total[q] > 0 ? (double)hits / (double)n_rel_total[q] : 0.0;                  // recall@k
+        per_query[(size_t)w * nq + q] = v;
+    }
+}
+
+// one CTA per weight vector: fixed-order sum over the queries / n_judged; the last CTA to finish picks the first best
+__global__ void __launch_bounds__(THREADS)
+grid_reduce_kernel(const double* __restrict__ per_query, int W, int nq, int n_judged, double* __restrict__ out_metric, int* __restrict__ out_best,
+                   unsigned* __restrict__ done) {
+    __shared__ double red[THREADS];
+    __shared__ bool last;
+    const int w = blockIdx.x;
+    double s = 0.0;
+    for (int q = threadIdx.x; q < nq; q += THREADS) s += per_query[(size_t)w * nq + q];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        out_metric[w] = s / (double)(n_judged > 0 ? n_judged : 1);
+        __threadfence();
+        last = atomicAdd(done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        int best = 0;
+        double best_v = -1.0;
+        for (int i = 0; i < W; i++) {
+            const double v = reinterpret_cast<volatile double*>(out_metric)[i];
+            if (v > best_v + 1e-15) { best_v = v; best = i; }  // first best wins, like ranx.optimize_fusion
+        }
+        *out_best = best;
+        *done = 0;
+    }
+}
+
 }  // namespace fuse
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int pow2_ge_host(int x) { int p = 2; while (p < x) p <<= 1; return p; }
 
 size_t fuse_workspace_bytes(int n_runs, int nq, int k_in) {
     const size_t E = (size_t)n_runs * k_in;
@@ -314,31 +463,115 @@ size_t fuse_workspace_bytes(int n_runs, int nq, int k_in) {
            align256((size_t)3 * n_runs * fuse::GSTATS_BLOCKS * sizeof(double));
 }
 
+struct FuseWs {
+    double* mat;
+    long long* doc;
+    int* ucount;
+    double* gstats;
+    double* partial;
+    uint8_t* end;
+};
+
+static FuseWs carve(void* workspace, int R, int nq, int E) {
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    FuseWs f;
+    f.mat = reinterpret_cast<double*>(w);
+    w += align256((size_t)nq * E * R * sizeof(double));
+    f.doc = reinterpret_cast<long long*>(w);
+    w += align256((size_t)nq * E * sizeof(long long));
+    f.ucount = reinterpret_cast<int*>(w);
+    w += align256((size_t)nq * sizeof(int));
+    f.gstats = reinterpret_cast<double*>(w);
+    w += align256((size_t)2 * R * sizeof(double));
+    f.partial = reinterpret_cast<double*>(w);
+    w += align256((size_t)3 * R * fuse::GSTATS_BLOCKS * sizeof(double));
+    f.end = w;
+    return f;
+}
+
+// union + default-minimum fill (+ global statistics for gzmuv): the part of a fusion that does not depend on the weights
+static int fuse_front(const double* scores, const long long* ids, const FuseParams& fp, const FuseWs& f, cudaStream_t stream) {
+    const int R = fp.n_runs, nq = fp.nq, k_in = fp.k_in, E = R * k_in;
+    const size_t smem_u = (size_t)pow2_ge_host(E) * sizeof(uint64_t);
+    static size_t attr_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (smem_u > 40 * 1024 && smem_u > attr_dev[dev_ & 63]) {  // static shared memory counts towards the 48 KB default limit
+        cudaError_t e = cudaFuncSetAttribute(fuse::union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u);
+        if (e != cudaSuccess) return -(int)e;
+        attr_dev[dev_ & 63] = smem_u;
+    }
+    fuse::union_kernel<<<nq, fuse::THREADS, smem_u, stream>>>(scores, ids, R, nq, k_in, fp.defmin, f.mat, f.doc, f.ucount);
+    if (fp.norm == 2) {
+        const int nb = nq < fuse::GSTATS_BLOCKS ? nq : fuse::GSTATS_BLOCKS;
+        fuse::gstats_partial_kernel<<<dim3(nb, R), fuse::THREADS, 0, stream>>>(f.mat, f.ucount, R, nq, E, f.partial);
+        fuse::gstats_final_kernel<<<R, 32, 0, stream>>>(f.partial, nb, f.gstats);
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+static bool fuse_shape_ok(const FuseParams& fp) {
+    const long long E = (long long)fp.n_runs * fp.k_in;
+    return fp.n_runs >= 1 && fp.n_runs <= fuse::R_MAX && fp.k_in >= 1 && fp.k_in <= 65535 && E <= fuse::E_MAX && fp.norm >= 0 && fp.norm <= 3;
+}
+
 int fuse_launch(const double* scores, const long long* ids, const double* weights, const FuseParams& fp,
                 double* out_scores, long long* out_ids, int* out_counts, void* workspace, size_t ws_bytes, cudaStream_t stream) {
     const int R = fp.n_runs, nq = fp.nq, k_in = fp.k_in;
     const int E = R * k_in;
-    if (R < 1 || R > fuse::R_MAX || k_in < 1 || k_in > 65535 || E > fuse::E_MAX || fp.norm < 0 || fp.norm > 3) return -3;
+    if (!fuse_shape_ok(fp)) return -3;
     if (nq <= 0) return 0;
     if (ws_bytes < fuse_workspace_bytes(R, nq, k_in)) return -4;
-    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
-    double* mat = reinterpret_cast<double*>(w);
-    w += align256((size_t)nq * E * R * sizeof(double));
-    long long* doc = reinterpret_cast<long long*>(w);
-    w += align256((size_t)nq * E * sizeof(long long));
-    int* ucount = reinterpret_cast<int*>(w);
-    w += align256((size_t)nq * sizeof(int));
-    double* gstats = reinterpret_cast<double*>(w);
-    w += align256((size_t)2 * R * sizeof(double));
-    double* partial = reinterpret_cast<double*>(w);
-    fuse::union_kernel<<<nq, fuse::THREADS, 0, stream>>>(scores, ids, R, nq, k_in, fp.defmin, mat, doc, ucount);
-    if (fp.norm == 2) {
-        const int nb = nq < fuse::GSTATS_BLOCKS ? nq : fuse::GSTATS_BLOCKS;
-        fuse::gstats_partial_kernel<<<dim3(nb, R), fuse::THREADS, 0, stream>>>(mat, ucount, R, nq, E, partial);
-        fuse::gstats_final_kernel<<<R, 32, 0, stream>>>(partial, nb, gstats);
+    const FuseWs f = carve(workspace, R, nq, E);
+    int rc = fuse_front(scores, ids, fp, f, stream);
+    if (rc) return rc;
+    const size_t smem_c = (size_t)pow2_ge_host(E) * (sizeof(uint64_t) + sizeof(uint32_t));
+    static size_t attr_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (smem_c > 40 * 1024 && smem_c > attr_dev[dev_ & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(fuse::combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+        if (e != cudaSuccess) return -(int)e;
+        attr_dev[dev_ & 63] = smem_c;
     }
-    fuse::combine_kernel<<<nq, fuse::THREADS, 0, stream>>>(mat, doc, ucount, weights, gstats, R, nq, E, fp.norm, out_scores, out_ids, out_counts);
+    fuse::combine_kernel<<<nq, fuse::THREADS, smem_c, stream>>>(f.mat, f.doc, f.ucount, weights, f.gstats, R, nq, E, fp.norm, out_scores, out_ids, out_counts);
     cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+size_t fuse_grid_workspace_bytes(int n_runs, int nq, int k_in, int n_weights) {
+    return fuse_workspace_bytes(n_runs, nq, k_in) + align256((size_t)nq * fuse::REL_MAX * sizeof(int)) + align256((size_t)nq * sizeof(int)) +
+           align256((size_t)n_weights * nq * sizeof(double)) + 256;
+}
+
+int fuse_grid_launch(const double* scores, const long long* ids, const FuseParams& fp, const double* weights, int n_weights, const long long* rel,
+                     int max_rel, const int* n_rel_total, int n_judged, int metric, int cut, double* out_metric, int* out_best, void* workspace,
+                     size_t ws_bytes, cudaStream_t stream) {
+    const int R = fp.n_runs, nq = fp.nq, k_in = fp.k_in;
+    const int E = R * k_in;
+    if (!fuse_shape_ok(fp) || n_weights < 1 || max_rel < 1 || metric < 0 || metric > 3) return -3;
+    if (nq <= 0) return 0;
+    if (ws_bytes < fuse_grid_workspace_bytes(R, nq, k_in, n_weights)) return -4;
+    const FuseWs f = carve(workspace, R, nq, E);
+    uint8_t* w = f.end;
+    int* rel_pos = reinterpret_cast<int*>(w);
+    w += align256((size_t)nq * fuse::REL_MAX * sizeof(int));
+    int* rel_cnt = reinterpret_cast<int*>(w);
+    w += align256((size_t)nq * sizeof(int));
+    double* per_query = reinterpret_cast<double*>(w);
+    w += align256((size_t)n_weights * nq * sizeof(double));
+    unsigned* done = reinterpret_cast<unsigned*>(w);
+    cudaError_t e = cudaMemsetAsync(done, 0, sizeof(unsigned), stream);
+    if (e != cudaSuccess) return -(int)e;
+    int rc = fuse_front(scores, ids, fp, f, stream);
+    if (rc) return rc;
+    fuse::grid_prepare_kernel<<<nq, fuse::THREADS, 0, stream>>>(f.mat, f.doc, f.ucount, f.gstats, R, nq, E, fp.norm, rel, max_rel, rel_pos, rel_cnt);
+    const int warps = fuse::THREADS / 32;
+    fuse::grid_eval_kernel<<<dim3(nq, (n_weights + warps - 1) / warps), fuse::THREADS, 0, stream>>>(f.mat, f.doc, f.ucount, weights, n_weights, R, nq, E,
+                                                                                                 rel_pos, rel_cnt, n_rel_total, metric, cut, per_query);
+    fuse::grid_reduce_kernel<<<n_weights, fuse::THREADS, 0, stream>>>(per_query, n_weights, nq, n_judged, out_metric, out_best, done);
+    e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
 }
 

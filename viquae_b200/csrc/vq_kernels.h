@@ -81,15 +81,6 @@ int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long 
                     const F32Plan& plan, int tile_begin, int tile_end, int map_stride, int map_ratio, const float* init_thr,
                     const float* ub_score, const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream);
 
-// ---- K2: small-batch HBM-streaming contraction + fused top-k (vq_stream.cu)
-struct StreamPlan {
-    int n_ctas, nq_pad, n_chunks;
-    long long rows_per_cta;
-};
-void stream_plan(int nq, long long n_rows, int n_sms, StreamPlan* plan);
-int stream_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
-                       const StreamPlan& plan, uint64_t* lists, int* counts, cudaStream_t stream);
-
 // ---- K4: merges (vq_merge.cu)
 // Merge step of one pass.  Candidate lists are [set][nq_pad][VQ_CAP] raw pairs + counts[set][nq_pad]; set 0 is
 // the RUNNING merged top-k of all passes so far.  Gathers set 0 (if use_set0) + sets [set_begin, set_begin+n_sets),
@@ -130,6 +121,12 @@ int expand_hits_launch(const float* scores, const long long* ids, int nq, int k_
                        const long long* map_targets, int many2one_max, int k, int out_cap, double* out_scores, long long* out_ids,
                        int* out_counts, int* overflow, cudaStream_t stream);
 
+// ---- adjacent rows (vq_inbatch.cu): in-batch similarity of the bi-encoder evaluation step; hard-negative marking
+int inbatch_launch(const void* q, const void* c, int dtype, int n_q, int n_c, int d, const long long* labels, long long ignore_index,
+                   float* log_probs, float* nll, int* rank, cudaStream_t stream);
+int mark_relevant_launch(const long long* ids, int nq, int k, const long long* rel_off, const long long* rel_ids, unsigned char* is_rel,
+                         cudaStream_t stream);
+
 // ---- K5: score fusion (vq_fuse.cu)
 struct FuseParams {
     int n_runs, nq, k_in, u_max;
@@ -139,5 +136,12 @@ struct FuseParams {
 size_t fuse_workspace_bytes(int n_runs, int nq, int k_in);
 int fuse_launch(const double* scores, const long long* ids, const double* weights, const FuseParams& fp,
                 double* out_scores, long long* out_ids, int* out_counts, void* workspace, size_t ws_bytes, cudaStream_t stream);
+// grid search of Fusion.fit: every weight vector of weights[n_weights][n_runs] evaluated against the relevant documents
+// rel[nq][max_rel] (doc ids, < 0 padding); metric 0 mrr, 1 precision, 2 hit_rate, 3 recall, all @cut (0 = no cut);
+// out_metric[n_weights] = mean over n_judged queries, out_best = index of the first best weight vector
+size_t fuse_grid_workspace_bytes(int n_runs, int nq, int k_in, int n_weights);
+int fuse_grid_launch(const double* scores, const long long* ids, const FuseParams& fp, const double* weights, int n_weights, const long long* rel,
+                     int max_rel, const int* n_rel_total, int n_judged, int metric, int cut, double* out_metric, int* out_best, void* workspace,
+                     size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace vq

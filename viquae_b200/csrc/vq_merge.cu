@@ -9,6 +9,8 @@
 #include "vq_common.cuh"
 #include "vq_kernels.h"
 
+#include <stdlib.h>
+
 namespace vq {
 
 // largest float strictly below x (x finite; -FLT_MAX stays)
@@ -54,9 +56,10 @@ __device__ __forceinline__ void merge_top128(uint64_t (&a)[4], const uint64_t (&
     }
 }
 
-// folds `n` keys at keys[0..n) into the warp's running top-128: warp w takes the 256-key chunks w, w+8, ...
+// folds `n` keys at keys[0..n) into the warp's running top-128: warp w takes the 256-key chunks w, w+WARPS, ...
+template <int WARPS = MERGE_WARPS>
 __device__ __forceinline__ void fold_chunks(const uint64_t* keys, int n, uint64_t (&run)[4], int warp, int lane) {
-    for (int c0 = warp * 256; c0 < n; c0 += MERGE_WARPS * 256) {
+    for (int c0 = warp * 256; c0 < n; c0 += WARPS * 256) {
         uint64_t ch[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
@@ -69,12 +72,13 @@ __device__ __forceinline__ void fold_chunks(const uint64_t* keys, int n, uint64_
     }
 }
 
-// 8 per-warp top-128 sets -> warp 0 holds the CTA-wide top-128 (sorted).  wtop: [8][128] keys of shared memory.
+// WARPS per-warp top-128 sets -> warp 0 holds the CTA-wide top-128 (sorted).  wtop: [WARPS][128] keys of shared memory.
+template <int WARPS = MERGE_WARPS>
 __device__ __forceinline__ void tree_merge(uint64_t* wtop, uint64_t (&run)[4], int warp, int lane) {
 #pragma unroll
     for (int r = 0; r < 4; r++) wtop[warp * 128 + r * 32 + lane] = run[r];
     __syncthreads();
-    for (int step = 1; step < MERGE_WARPS; step <<= 1) {
+    for (int step = 1; step < WARPS; step <<= 1) {
         if ((warp & (2 * step - 1)) == 0) {
             uint64_t other[4];
 #pragma unroll
@@ -92,11 +96,15 @@ __device__ __forceinline__ void tree_merge(uint64_t* wtop, uint64_t (&run)[4], i
 // 256-key chunks in registers and keeps a running top-128; a 3-level tree leaves the CTA-wide top-128 in
 // warp 0, which writes the best k back to set 0 (sorted raw pairs + count), the k-th score to thr_out (the
 // primed threshold of the next pass) and, for the last pass, the final (scores, ids).
-__global__ void __launch_bounds__(MERGE_THREADS)
+// T threads per CTA: 256 (lowest latency per query) or 128 (twice as many CTAs resident: one wave at 1,250 queries,
+// where 256-thread CTAs need a second, almost empty wave)
+template <int T>
+__global__ void __launch_bounds__(T)
 merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int use_set0, int set_begin, int n_sets, int nq_pad, int k,
                    long long id_offset, float* __restrict__ thr_out, float* __restrict__ out_scores, long long* __restrict__ out_ids,
                    int cap) {
-    extern __shared__ uint64_t keys[];           // [cap] gathered keys, then [8][128] for the tree
+    constexpr int MERGE_THREADS = T, MERGE_WARPS = T / 32;
+    extern __shared__ uint64_t keys[];           // [cap] gathered keys, then [WARPS][128] for the tree
     __shared__ int off_s[MERGE_MAX_SETS + 2];     // exclusive prefix sums of the list lengths (index 0 = set 0)
     __shared__ int warp_tot[MERGE_WARPS];
     __shared__ int round_end;
@@ -176,11 +184,11 @@ merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int u
             }
         }
         __syncthreads();
-        fold_chunks(keys, n_round, run, warp, lane);
+        fold_chunks<MERGE_WARPS>(keys, n_round, run, warp, lane);
         __syncthreads();
         l0 = l1;
     }
-    tree_merge(keys, run, warp, lane);
+    tree_merge<MERGE_WARPS>(keys, run, warp, lane);
     if (warp == 0) {
         const int have = total < k ? total : k;
         uint64_t* dst = lists + (size_t)q * VQ_CAP;  // set 0
@@ -303,26 +311,40 @@ static int pick_cap(long long total, int k) {
     return cap;
 }
 
-int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
-                       float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream) {
-    if (nq <= 0) return 0;
-    if (n_sets + 1 > MERGE_MAX_SETS) return -2;
-    // capacity: at least one full list + the running top-k must fit
-    const int cap = pick_cap(expected_total, VQ_CAP);
-    const size_t smem = (size_t)cap * sizeof(uint64_t);
+template <int T>
+static int merge_lists_launch_t(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
+                                float* thr_out, float* out_scores, long long* out_ids, int cap, cudaStream_t stream) {
     static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
     int dev_ = 0;
     cudaGetDevice(&dev_);
     bool& attr_set = attr_set_dev[dev_ & 63];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP_MAX * 8);
+        cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP_MAX * 8);
         if (e != cudaSuccess) return -(int)e;
         attr_set = true;
     }
-    merge_lists_kernel<<<nq, MERGE_THREADS, smem, stream>>>(lists, counts, use_set0, set_begin, n_sets, nq_pad, k, id_offset, thr_out, out_scores,
-                                                           out_ids, cap);
+    merge_lists_kernel<T><<<nq, T, (size_t)cap * sizeof(uint64_t), stream>>>(lists, counts, use_set0, set_begin, n_sets, nq_pad, k, id_offset, thr_out,
+                                                                         out_scores, out_ids, cap);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
+}
+
+int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
+                       float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream) {
+    if (nq <= 0) return 0;
+    if (n_sets + 1 > MERGE_MAX_SETS) return -2;
+    // capacity: at least one full list + the running top-k must fit (larger totals take several gather rounds)
+    const int cap = pick_cap(expected_total, VQ_CAP);
+    // 256-thread CTAs: 8 resident per SM (1,184 on 148 SMs).  More queries than that would leave a second, nearly empty
+    // wave: 128-thread CTAs (16 per SM) keep it to one.
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("VQ_MERGE_THREADS");
+        forced = e ? atoi(e) : 0;
+    }
+    const bool small = forced ? forced == 128 : (nq > 1184 && nq <= 2368 && cap <= 2048);
+    if (small) return merge_lists_launch_t<128>(lists, counts, use_set0, set_begin, n_sets, nq_pad, nq, k, id_offset, thr_out, out_scores, out_ids, cap, stream);
+    return merge_lists_launch_t<256>(lists, counts, use_set0, set_begin, n_sets, nq_pad, nq, k, id_offset, thr_out, out_scores, out_ids, cap, stream);
 }
 
 int merge_topk_launch(const float* scores, const long long* ids, long long stride_s, long long stride_i, int n_lists, int nq, int k_in,

@@ -26,8 +26,6 @@ namespace vq {
 namespace xchg {
 
 constexpr int PUBLISH_THREADS = 256;
-constexpr int MERGE_THREADS = 256;
-constexpr int MERGE_WARPS = MERGE_THREADS / 32;
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
@@ -120,10 +118,13 @@ __device__ __forceinline__ void merge_top128(uint64_t (&a)[4], const uint64_t (&
 
 // One CTA per query: wait for the flags, pull the query's k_in entries of every rank's published list from the
 // peers' slots (scores f32 [nq, k_in] then ids i64 [nq, k_in] at ids_off), merge to the global top k_out.
-__global__ void __launch_bounds__(MERGE_THREADS)
+// T threads per CTA: 256, or 128 when that keeps all queries in one wave (see merge_lists_launch).
+template <int T>
+__global__ void __launch_bounds__(T)
 pull_merge_kernel(const XchgControl* ctl, XchgPeers peers, size_t slot_bytes, size_t ids_off, int world, int nq, int k_in, int k_out,
                   float* __restrict__ out_scores, long long* __restrict__ out_ids) {
-    extern __shared__ uint64_t keys[];  // [cap] gathered keys, reused as [8][128] by the tree
+    constexpr int MERGE_THREADS = T, MERGE_WARPS = T / 32;
+    extern __shared__ uint64_t keys[];  // [cap] gathered keys, reused as [WARPS][128] by the tree
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned want = ctl->seq;  // this rank published `want` earlier on this stream
@@ -213,6 +214,22 @@ int xchg_publish_launch(XchgControl* ctl, uint8_t* slots, size_t slot_bytes, con
     return e == cudaSuccess ? 0 : -(int)e;
 }
 
+template <int T>
+static int xchg_merge_launch_t(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, size_t ids_off, int cap, int world, int nq, int k_in,
+                               int k_out, float* out_scores, long long* out_ids, cudaStream_t stream) {
+    static bool attr_set_dev[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set_dev[dev_ & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(xchg::pull_merge_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+        if (e != cudaSuccess) return -(int)e;
+        attr_set_dev[dev_ & 63] = true;
+    }
+    xchg::pull_merge_kernel<T><<<nq, T, (size_t)cap * 8, stream>>>(ctl, peers, slot_bytes, ids_off, world, nq, k_in, k_out, out_scores, out_ids);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
 int xchg_merge_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, int world, int nq, int k_in, int k_out,
                       float* out_scores, long long* out_ids, cudaStream_t stream) {
     if (nq <= 0) return 0;
@@ -220,18 +237,9 @@ int xchg_merge_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slo
     int cap = 1024;
     while (cap < world * k_in) cap <<= 1;
     const size_t ids_off = ((size_t)nq * k_in * 4 + 7) / 8 * 8;
-    static bool attr_set_dev[64] = {};
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!attr_set_dev[dev_ & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(xchg::pull_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
-        if (e != cudaSuccess) return -(int)e;
-        attr_set_dev[dev_ & 63] = true;
-    }
-    xchg::pull_merge_kernel<<<nq, xchg::MERGE_THREADS, (size_t)cap * 8, stream>>>(ctl, peers, slot_bytes, ids_off, world, nq, k_in, k_out, out_scores,
-                                                                               out_ids);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : -(int)e;
+    if (nq > 1184 && nq <= 2368 && cap <= 2048)
+        return xchg_merge_launch_t<128>(ctl, peers, slot_bytes, ids_off, cap, world, nq, k_in, k_out, out_scores, out_ids, stream);
+    return xchg_merge_launch_t<256>(ctl, peers, slot_bytes, ids_off, cap, world, nq, k_in, k_out, out_scores, out_ids, stream);
 }
 
 int xchg_gather_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, int world, size_t bytes, void* dst, cudaStream_t stream) {

@@ -5,7 +5,8 @@ Same constructor / method names and kwargs as the reference's ``Fusion`` (meerqa
 ``.test(best_params, metrics)``, plus the module-level ``default_minimum`` (fuse.py:132-149) and
 ``gzmuv_norm`` (fuse.py:86-129).  All score arithmetic (default-minimum fill, (g)zmuv / min-max
 normalisation, weighted sum, descending sort) runs on the GPU in float64 through ``vq_fuse``; the
-host only converts between the reference's dict runs and dense ``[n_runs, nq, k]`` arrays.
+host only converts between the reference's dict runs and dense ``[n_runs, nq, k]`` arrays.  ``Fusion.fit``'s
+grid search over weight vectors is one device pass too (``vq_fuse_grid``).
 
 Supported: ``method="wsum"`` with ``norm in {"zmuv", "gzmuv", "min-max", None}`` — the combinations
 the shipped experiment configs use.  ranx's other norms/methods raise ``NotImplementedError``.
@@ -189,64 +190,63 @@ class Fusion:
         # defmin precedes normalisation (fuse.py:183-184 vs :199-200,224-225): the kernel applies them in that order
         return _fuse_runs(self.runs, weights, norm=norm, defmin=self.defmin, name="fusion", device=self.device)
 
-    def _dense_metric(self, dense, rel, out_i, out_c, metric):
-        """mrr@k / precision@k / hit_rate@k / recall@k of a fused dense ranking, on the device (evaluation only:
-        the grid search of fit() calls it once per weight combination).  rel: [nq, max_rel] relevant doc codes, -2 pad."""
-        import torch
-
-        name, _, cut = metric.partition("@")
-        kk = int(cut) if cut else out_i.shape[1]
-        ranked = out_i[:, :kk]
-        hit = (ranked[:, :, None] == rel[:, None, :]).any(-1) & (torch.arange(ranked.shape[1], device=ranked.device)[None, :] < out_c[:, None])
-        judged = (rel >= 0).any(-1)  # queries that have qrels (ranx averages over the qrels' queries)
-        n_judged = int(self._n_qrels_queries)
-        if name == "mrr":
-            first = torch.where(hit.any(-1), hit.float().argmax(-1), torch.full_like(out_c, -1, dtype=torch.int64))
-            v = torch.where(first >= 0, 1.0 / (first.double() + 1.0), torch.zeros_like(first, dtype=torch.float64))
-        elif name == "precision":
-            v = hit.sum(-1).double() / float(kk)
-        elif name == "hit_rate":
-            v = hit.any(-1).double()
-        elif name == "recall":
-            v = hit.sum(-1).double() / (rel >= 0).sum(-1).clamp(min=1).double()
-        else:
-            raise ValueError(f"unsupported metric {metric!r}")
-        return float((v * judged).sum().item()) / max(n_judged, 1)
+    METRIC_CODES = {"mrr": 0, "precision": 1, "hit_rate": 2, "recall": 3}
 
     def fit(self, metric: str = "mrr@100"):
-        """Finds the best weights on the 0.1 grid for every (norm, method); writes ``{norm}_{method}_best_params.yaml``.
-        The runs are converted to dense arrays once; every grid point is one ``vq_fuse`` call + an on-device metric."""
+        """Finds the best weights on the 0.1 grid for every (norm, method) (fuse.py:193-217 -> ranx.optimize_fusion);
+        writes ``{norm}_{method}_best_params.yaml``.  One ``vq_fuse_grid`` call per (norm, method): union +
+        default-minimum + normalisation once, then all 11 / 66 / 286 weight vectors are scored on the device from the
+        ranks of the relevant documents; the host only builds the dense arrays and reads back ``[n_weights]`` metric
+        values and the index of the first best."""
         import torch
 
         if self.qrels is None:
             raise ValueError("Fusion.fit needs qrels")
         norms = [self.norm] if self.norm is None or isinstance(self.norm, str) else self.norm
         methods = [self.method] if self.method is None or isinstance(self.method, str) else self.method
+        name, _, cut = metric.partition("@")
+        if name not in self.METRIC_CODES:
+            raise ValueError(f"unsupported metric {metric!r}: the device grid search scores {sorted(self.METRIC_CODES)} (@k)")
+        cut = int(cut) if cut else 0
         dense = DenseRuns(self.runs)
         dev = torch.device(f"cuda:{self.device}")
         d_scores = torch.from_numpy(dense.scores).to(dev)
         d_ids = torch.from_numpy(dense.ids).to(dev)
+        R, nq, k_in = dense.scores.shape
         qrels = self.qrels.qrels
-        self._n_qrels_queries = len(qrels)
-        max_rel = max([sum(1 for g in rels.values() if g > 0) for rels in qrels.values()] + [1])
-        rel = np.full((len(dense.q_ids), max_rel), -2, dtype=np.int64)
-        for qi, q in enumerate(dense.q_ids):
-            codes = [dense._encode[d] for d, g in qrels.get(q, {}).items() if g > 0 and d in dense._encode]
-            rel[qi, :len(codes)] = codes
-            if q in qrels and not codes:
-                rel[qi, 0] = 2 ** 62  # judged query whose relevant documents were never retrieved: counts as 0
-        rel = torch.from_numpy(rel).to(dev)
+        codes = [[dense._encode[d] for d, g in qrels.get(q, {}).items() if g > 0 and d in dense._encode] for q in dense.q_ids]
+        max_rel = max([len(c) for c in codes] + [1])
+        if max_rel > 256:
+            raise NotImplementedError(f"a query has {max_rel} relevant documents among the retrieved ones; the device grid search holds 256 per query")
+        rel = np.full((nq, max_rel), -1, dtype=np.int64)
+        for qi, c in enumerate(codes):
+            rel[qi, :len(c)] = c
+        n_rel_total = np.array([sum(1 for g in qrels.get(q, {}).values() if g > 0) for q in dense.q_ids], dtype=np.int32)
+        d_rel = torch.from_numpy(rel).to(dev)
+        d_nrel = torch.from_numpy(n_rel_total).to(dev)
+        grid = list(weight_grid(R))
+        d_w = torch.tensor(grid, dtype=torch.float64, device=dev)
+        W = len(grid)
+        lib = _lib.load()
+        ws = torch.empty(lib.vq_fuse_grid_workspace_bytes(R, nq, k_in, W) + 256, dtype=torch.uint8, device=dev)
+        out_metric = torch.empty((W,), dtype=torch.float64, device=dev)
+        out_best = torch.zeros((1,), dtype=torch.int32, device=dev)
         results = {}
+        self.grid_reports = {}
         for norm in norms:
+            if norm not in NORM_CODES:
+                raise NotImplementedError(f"norm {norm!r}: the B200 fusion kernel implements {sorted(k for k in NORM_CODES if k)} and None")
             for method in methods:
                 self._check_method(method)
-                best, best_score, report = None, -1.0, []
-                for weights in weight_grid(len(self.runs)):
-                    _, out_i, out_c = fuse_dense(d_scores, d_ids, weights, norm=norm, defmin=self.defmin, device=self.device)
-                    score = self._dense_metric(dense, rel, out_i, out_c.long(), metric)
-                    report.append((weights, score))
-                    if score > best_score + 1e-15:  # first best wins, like ranx
-                        best, best_score = weights, score
+                with torch.cuda.device(dev):
+                    _lib.check(lib.vq_fuse_grid(d_scores.data_ptr(), d_ids.data_ptr(), R, nq, k_in, int(self.defmin), NORM_CODES[norm],
+                                                d_w.data_ptr(), W, d_rel.data_ptr(), max_rel, d_nrel.data_ptr(), len(qrels),
+                                                self.METRIC_CODES[name], cut, out_metric.data_ptr(), out_best.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+                scores = out_metric.cpu().numpy()
+                best_i = int(out_best.item())
+                best, best_score = grid[best_i], float(scores[best_i])
+                self.grid_reports[(norm, method)] = list(zip(grid, scores.tolist()))
                 best_params = {"weights": [round(w, 10) for w in best]}
                 results[(norm, method)] = (best_params, best_score)
                 print(f"Norm: {norm}, Method: {method}. Best parameters: {best_params}. {metric}={best_score:.4f}")

@@ -51,7 +51,7 @@ _DTYPES = {"f32": _lib.F32, "fp32": _lib.F32, "float32": _lib.F32, "bf16": _lib.
            "f16": _lib.F16, "fp16": _lib.F16, "float16": _lib.F16, "f32x3": _lib.F32X3}
 _WIDE = (_lib.F32, _lib.F32X3)  # storage types that hold full fp32 values
 _VARIANTS = {None: _lib.VARIANT_AUTO, "auto": _lib.VARIANT_AUTO, "tc_cg1": _lib.VARIANT_TC_CG1,
-             "tc_cg2": _lib.VARIANT_TC_CG2, "stream": _lib.VARIANT_STREAM}
+             "tc_cg2": _lib.VARIANT_TC_CG2}
 
 
 def parse_string_factory(string_factory: Optional[str], metric_type: Optional[int]) -> bool:
