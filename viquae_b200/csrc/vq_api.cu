@@ -135,9 +135,10 @@ static void host_copy(void* dst, const void* src, size_t bytes) {
 }
 
 // [n, d] rows of src_dtype -> the index's storage layout (corpus rows, or the query-side arrangement of VQ_F32X3)
-static int to_storage(const vq_index* idx, const void* src, int src_dtype, void* dst, long long n, int l2norm, int query_side, cudaStream_t s) {
-    if (idx->dtype == VQ_F32X3) return vq::split_rows_launch(src, src_dtype, idx->d, dst, idx->seg, n, idx->d, l2norm, query_side, s);
-    return vq::prep_rows_launch(src, src_dtype, idx->d, dst, idx->dtype, idx->ld, n, idx->d, l2norm, s);
+static int to_storage(const vq_index* idx, const void* src, int src_dtype, void* dst, long long n, int l2norm, int query_side, cudaStream_t s,
+                      long long n_pad = 0) {
+    if (idx->dtype == VQ_F32X3) return vq::split_rows_launch(src, src_dtype, idx->d, dst, idx->seg, n, idx->d, l2norm, query_side, s, n_pad);
+    return vq::prep_rows_launch(src, src_dtype, idx->d, dst, idx->dtype, idx->ld, n, idx->d, l2norm, s, n_pad);
 }
 
 // stored corpus rows -> [n, d] rows of dst_dtype
@@ -578,14 +579,11 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     if (workspace_bytes < need) return fail(VQ_ERR_NOMEM, "vq_index_search: workspace %zu < %zu bytes", workspace_bytes, need);
     uint8_t* ws = (uint8_t*)workspace;
     void* qprep = ws + sp.off_q;
-    int rc = to_storage(idx, q, q_dtype, qprep, nq, l2norm_q ? 1 : 0, 1, s);
+    // rows [nq, nq_pad) of the prepared query matrix are real zero rows (written by the same kernel), so the tensor-core
+    // path never depends on TMA out-of-bounds fill for the query operand
+    int rc = to_storage(idx, q, q_dtype, qprep, nq, l2norm_q ? 1 : 0, 1, s, sp.nq_pad);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
     idx->launches += 1;
-    // rows [nq, nq_pad) of the prepared query matrix are real zero rows, so the tensor-core path never
-    // depends on TMA out-of-bounds fill for the query operand
-    if (sp.nq_pad > nq)
-        CUDA_TRY(cudaMemsetAsync((uint8_t*)qprep + (size_t)nq * idx->ld * esize(idx->dtype), 0,
-                                 (size_t)(sp.nq_pad - nq) * idx->ld * esize(idx->dtype), s));
     const bool timed = idx->timing && idx->n_timed < VQ_TIMING_SLOTS && idx->ntotal;
     if (timed) CUDA_TRY(cudaEventRecord(idx->ev0[idx->n_timed], s));
     if (k <= VQ_KMAX) {

@@ -13,14 +13,15 @@ namespace vq {
 // ---- K0: ingest / query preparation (vq_prep.cu)
 // src [n, d] (src_dtype, row stride ld_src) -> dst [n, ld_dst] (dst_dtype); optional row L2-normalisation;
 // columns d..ld_dst-1 are zero-filled.
+// rows [n, n_pad) of dst (if n_pad > n) are written as zero rows (the padded query operand of the tensor-core path)
 int prep_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
-                     long long n, int d, int l2norm, cudaStream_t stream);
+                     long long n, int d, int l2norm, cudaStream_t stream, long long n_pad = 0);
 // VQ_F32X3 storage: [n, 6*seg] bf16 per row, six segments of seg columns.  Corpus side: lo hi mid mid hi hi;
 // query side: hi lo mid hi mid hi (segment s of a query row times segment s of a corpus row are the six product terms,
 // smallest first).  split: src rows -> segments (optional L2 normalisation first, same arithmetic as prep_rows);
 // join: corpus-side segments -> hi + (mid + lo), exactly the fp32 value that was split.
 int split_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int seg, long long n, int d, int l2norm,
-                      int query_side, cudaStream_t stream);
+                      int query_side, cudaStream_t stream, long long n_pad = 0);
 int join_rows_launch(const void* src, int seg, void* dst, int dst_dtype, long long ld_dst, long long n, int d, cudaStream_t stream);
 
 

@@ -23,12 +23,17 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return
 
 template <typename S, typename D>
 __global__ void __launch_bounds__(256)
-prep_rows_kernel(const S* __restrict__ src, long long ld_src, D* __restrict__ dst, long long ld_dst, long long n, int d, int l2norm) {
+prep_rows_kernel(const S* __restrict__ src, long long ld_src, D* __restrict__ dst, long long ld_dst, long long n, int d, int l2norm,
+                 long long n_pad) {
     const int lane = threadIdx.x & 31;
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps_total) {
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_pad; row += warps_total) {
         const S* s = src + row * ld_src;
         D* o = dst + row * ld_dst;
+        if (row >= n) {  // padding rows of a query operand: real zero rows
+            for (int j = lane; j < (int)ld_dst; j += 32) o[j] = from_f32<D>(0.0f);
+            continue;
+        }
         float inv_is_div = 1.0f;  // divisor
         if (l2norm) {
             float acc = 0.0f;
@@ -54,19 +59,20 @@ prep_rows_kernel(const S* __restrict__ src, long long ld_src, D* __restrict__ ds
 
 template <typename S>
 static int prep_dispatch_dst(const void* src, long long ld_src, void* dst, int dst_dtype, long long ld_dst, long long n, int d, int l2norm,
-                             cudaStream_t stream) {
-    long long blocks = (n + 7) / 8;
+                             long long n_pad, cudaStream_t stream) {
+    if (n_pad < n) n_pad = n;
+    long long blocks = (n_pad + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) return 0;
     switch (dst_dtype) {
         case VQ_DTYPE_F32:
-            prep_rows_kernel<S, float><<<(unsigned)blocks, 256, 0, stream>>>((const S*)src, ld_src, (float*)dst, ld_dst, n, d, l2norm);
+            prep_rows_kernel<S, float><<<(unsigned)blocks, 256, 0, stream>>>((const S*)src, ld_src, (float*)dst, ld_dst, n, d, l2norm, n_pad);
             break;
         case VQ_DTYPE_BF16:
-            prep_rows_kernel<S, __nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>((const S*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, n, d, l2norm);
+            prep_rows_kernel<S, __nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>((const S*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, n, d, l2norm, n_pad);
             break;
         case VQ_DTYPE_F16:
-            prep_rows_kernel<S, __half><<<(unsigned)blocks, 256, 0, stream>>>((const S*)src, ld_src, (__half*)dst, ld_dst, n, d, l2norm);
+            prep_rows_kernel<S, __half><<<(unsigned)blocks, 256, 0, stream>>>((const S*)src, ld_src, (__half*)dst, ld_dst, n, d, l2norm, n_pad);
             break;
         default:
             return -2;
@@ -87,12 +93,16 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& hi, __nv_bfloat16
 template <typename S>
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const S* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst, int seg, long long n, int d, int l2norm,
-                  int query_side) {
+                  int query_side, long long n_pad) {
     const int lane = threadIdx.x & 31;
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps_total) {
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_pad; row += warps_total) {
         const S* s = src + row * ld_src;
         __nv_bfloat16* o = dst + row * 6 * (long long)seg;
+        if (row >= n) {
+            for (int j = lane; j < 6 * seg; j += 32) o[j] = __float2bfloat16_rn(0.0f);
+            continue;
+        }
         float div = 1.0f;
         if (l2norm) {  // same arithmetic as prep_rows_kernel: the normalised fp32 values are those of an fp32 index
             float acc = 0.0f;
@@ -145,13 +155,14 @@ static unsigned row_blocks(long long n) {
 }
 
 int split_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int seg, long long n, int d, int l2norm,
-                      int query_side, cudaStream_t stream) {
-    if (n <= 0) return 0;
+                      int query_side, cudaStream_t stream, long long n_pad) {
+    if (n_pad < n) n_pad = n;
+    if (n_pad <= 0) return 0;
     __nv_bfloat16* o = (__nv_bfloat16*)dst;
     switch (src_dtype) {
-        case VQ_DTYPE_F32: split_rows_kernel<float><<<row_blocks(n), 256, 0, stream>>>((const float*)src, ld_src, o, seg, n, d, l2norm, query_side); break;
-        case VQ_DTYPE_BF16: split_rows_kernel<__nv_bfloat16><<<row_blocks(n), 256, 0, stream>>>((const __nv_bfloat16*)src, ld_src, o, seg, n, d, l2norm, query_side); break;
-        case VQ_DTYPE_F16: split_rows_kernel<__half><<<row_blocks(n), 256, 0, stream>>>((const __half*)src, ld_src, o, seg, n, d, l2norm, query_side); break;
+        case VQ_DTYPE_F32: split_rows_kernel<float><<<row_blocks(n_pad), 256, 0, stream>>>((const float*)src, ld_src, o, seg, n, d, l2norm, query_side, n_pad); break;
+        case VQ_DTYPE_BF16: split_rows_kernel<__nv_bfloat16><<<row_blocks(n_pad), 256, 0, stream>>>((const __nv_bfloat16*)src, ld_src, o, seg, n, d, l2norm, query_side, n_pad); break;
+        case VQ_DTYPE_F16: split_rows_kernel<__half><<<row_blocks(n_pad), 256, 0, stream>>>((const __half*)src, ld_src, o, seg, n, d, l2norm, query_side, n_pad); break;
         default: return -2;
     }
     cudaError_t e = cudaGetLastError();
@@ -172,11 +183,11 @@ int join_rows_launch(const void* src, int seg, void* dst, int dst_dtype, long lo
 }
 
 int prep_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
-                     long long n, int d, int l2norm, cudaStream_t stream) {
+                     long long n, int d, int l2norm, cudaStream_t stream, long long n_pad) {
     switch (src_dtype) {
-        case VQ_DTYPE_F32: return prep_dispatch_dst<float>(src, ld_src, dst, dst_dtype, ld_dst, n, d, l2norm, stream);
-        case VQ_DTYPE_BF16: return prep_dispatch_dst<__nv_bfloat16>(src, ld_src, dst, dst_dtype, ld_dst, n, d, l2norm, stream);
-        case VQ_DTYPE_F16: return prep_dispatch_dst<__half>(src, ld_src, dst, dst_dtype, ld_dst, n, d, l2norm, stream);
+        case VQ_DTYPE_F32: return prep_dispatch_dst<float>(src, ld_src, dst, dst_dtype, ld_dst, n, d, l2norm, n_pad, stream);
+        case VQ_DTYPE_BF16: return prep_dispatch_dst<__nv_bfloat16>(src, ld_src, dst, dst_dtype, ld_dst, n, d, l2norm, n_pad, stream);
+        case VQ_DTYPE_F16: return prep_dispatch_dst<__half>(src, ld_src, dst, dst_dtype, ld_dst, n, d, l2norm, n_pad, stream);
         default: return -2;
     }
 }
