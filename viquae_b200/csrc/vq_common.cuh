@@ -87,6 +87,107 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&key)[E], int l
     }
 }
 
+// 128 keys per warp, 4 per lane (element e = r*32 + lane), descending
+__device__ __forceinline__ void warp_bitonic_sort_desc4(uint64_t (&key)[4], int lane) {
+#pragma unroll 1
+    for (int s = 2; s <= 128; s <<= 1) {
+        if (s >= 128) bitonic_inreg_stage<4, 2>(key, s);
+        if (s >= 64) bitonic_inreg_stage<4, 1>(key, s);
+#pragma unroll 1
+        for (int j = (s >> 1) < 16 ? (s >> 1) : 16; j > 0; j >>= 1) {
+            const bool lower = (lane & j) == 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int e = r * 32 + lane;
+                const uint64_t other = __shfl_xor_sync(VQ_FULL_MASK, key[r], j);
+                const bool desc = ((e & s) == 0);
+                key[r] = (lower == desc) ? umax64(key[r], other) : umin64(key[r], other);
+            }
+        }
+    }
+}
+
+// Top-128 of up to 32*R keys held R per lane (0 = empty slot; keys are distinct), by SELECTION instead of sorting:
+// a bitwise search for the 128-th largest score word (one compare per key and bit, starting below the bits all keys
+// share), a second search over the row words only if exactly tied scores straddle the cut, ballot compaction of the
+// survivors into 128 shared-memory slots and ONE 128-key bitonic sort.  ~1/8 of the instructions of sorting every
+// 256-key chunk (the merge kernels are ALU-pipe bound: 64-bit compare + select per exchange).
+// out: sorted descending, 4 per lane (element e = r*32 + lane); slots: 128 uint64 of shared memory owned by the warp.
+template <int R>
+__device__ __forceinline__ void warp_select_top128(const uint64_t (&key)[R], uint64_t (&out)[4], uint64_t* slots, int lane) {
+    int nv = 0;
+    uint32_t mx = 0u, mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const uint32_t hi = (uint32_t)(key[r] >> 32);
+        const bool valid = key[r] != 0ull;
+        nv += valid ? 1 : 0;
+        mx = max(mx, hi);
+        mn = valid ? min(mn, hi) : mn;
+    }
+    nv = __reduce_add_sync(VQ_FULL_MASK, nv);
+    uint32_t T = 0u, Lw = 0u;  // keep: hi > T, or hi == T and lo >= Lw
+    if (nv > 128) {
+        mx = __reduce_max_sync(VQ_FULL_MASK, mx);
+        mn = __reduce_min_sync(VQ_FULL_MASK, mn);
+        const uint32_t diff = mx ^ mn;
+        uint32_t prefix = mx;
+        if (diff) {
+            const int top = 31 - __clz(diff);
+            prefix = top == 31 ? 0u : (mx & ~((2u << top) - 1u));   // the bits every key shares
+#pragma unroll 1
+            for (int b = top; b >= 0; b--) {
+                const uint32_t cand = prefix | (1u << b);
+                int c = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) c += ((uint32_t)(key[r] >> 32) >= cand) ? 1 : 0;
+                if (__reduce_add_sync(VQ_FULL_MASK, c) >= 128) prefix = cand;
+            }
+        }
+        T = prefix;  // count(hi >= T) >= 128 > count(hi > T)
+        int gt = 0, eq = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t hi = (uint32_t)(key[r] >> 32);
+            gt += hi > T ? 1 : 0;
+            eq += hi == T ? 1 : 0;
+        }
+        gt = __reduce_add_sync(VQ_FULL_MASK, gt);
+        eq = __reduce_add_sync(VQ_FULL_MASK, eq);
+        const int need = 128 - gt;  // >= 1
+        if (eq > need) {
+            // exactly tied scores straddle the cut: the `need` largest row words (= lowest ids) among them
+            uint32_t pl = 0u;
+#pragma unroll 1
+            for (int b = 31; b >= 0; b--) {
+                const uint32_t cand = pl | (1u << b);
+                int c = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) c += ((uint32_t)(key[r] >> 32) == T && (uint32_t)key[r] >= cand) ? 1 : 0;
+                if (__reduce_add_sync(VQ_FULL_MASK, c) >= need) pl = cand;
+            }
+            Lw = pl;
+        }
+    }
+    // compaction of the survivors (at most 128) into the warp's slots
+    const unsigned lt = (1u << lane) - 1u;
+    int base = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const uint32_t hi = (uint32_t)(key[r] >> 32), lo = (uint32_t)key[r];
+        const bool keep = key[r] != 0ull && (hi > T || (hi == T && lo >= Lw));
+        const unsigned m = __ballot_sync(VQ_FULL_MASK, keep);
+        if (keep) slots[base + __popc(m & lt)] = key[r];
+        base += __popc(m);
+    }
+    for (int e = base + lane; e < 128; e += 32) slots[e] = 0ull;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; r++) out[r] = slots[r * 32 + lane];
+    __syncwarp();
+    warp_bitonic_sort_desc4(out, lane);
+}
+
 // Warp-cooperative prune of one candidate list: sort its n (<= VQ_CAP) keys, keep the best
 // min(n, k) in place (sorted descending), return the new length.  thr_out = k-th score if the
 // list held at least k keys, else -FLT_MAX.  Called by all 32 lanes with identical arguments.

@@ -208,6 +208,109 @@ merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int u
     }
 }
 
+
+// ---- merge step of one pass by SELECTION, one WARP per query (the default; merge_lists_kernel is the sort-everything
+// restatement kept for A/B runs, VQ_MERGE_IMPL=sort).  Same contract as merge_lists_kernel.  The candidates are
+// taken in batches of whole lists (<= 1024 keys, 32 per lane); every batch is reduced to its top 128 by
+// warp_select_top128 and folded into the running top-128.  No block-level barrier: the warps of a CTA are independent.
+constexpr int SEL_R = 32;
+constexpr int SEL_BATCH = 32 * SEL_R;
+constexpr int SEL_WARPS = 4;
+
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+merge_select_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k,
+                    long long id_offset, float* __restrict__ thr_out, float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+    extern __shared__ uint64_t sel_smem[];                       // per warp: owner ids (u16 [SEL_BATCH] = 256 u64) + [128] slots
+    __shared__ int off_all[SEL_WARPS][MERGE_MAX_SETS + 2];        // exclusive prefix sums of the list lengths
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * SEL_WARPS + warp;
+    if (q >= nq) return;
+    uint64_t* slots = sel_smem + (size_t)warp * (256 + 128);
+    int* off = off_all[warp];
+    const int L = n_sets + 1;  // logical list l: 0 = running merged list (set 0), l >= 1 = set_begin + l - 1
+    // list lengths: every load is issued before the first one is used (the kernel is latency-bound on these round trips)
+    constexpr int CPL = (MERGE_MAX_SETS + 1 + 31) / 32;  // lists per lane (covers l = 0 .. MERGE_MAX_SETS), lane-major: lane owns l = lane * CPL + j
+    int c[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; j++) {
+        const int l = lane * CPL + j;
+        const int set = l == 0 ? 0 : set_begin + l - 1;
+        c[j] = (l >= L || (l == 0 && !use_set0)) ? 0 : __ldcg(counts + (size_t)set * nq_pad + q);
+    }
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < CPL; j++) mine += c[j];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(VQ_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(VQ_FULL_MASK, incl, 31);
+    {
+        int before = incl - mine;
+#pragma unroll
+        for (int j = 0; j < CPL; j++) {
+            const int l = lane * CPL + j;
+            if (l <= L) off[l] = before;
+            before += c[j];
+        }
+    }
+    __syncwarp();
+    uint16_t* owner = reinterpret_cast<uint16_t*>(slots);  // [SEL_BATCH] list of every staged element (reuses nothing live: slots are written later)
+    uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
+    int la = 0;
+    while (la < L && off[la] < total) {
+        const int base = off[la];
+        int lo = la + 1, hi = L;  // the most whole lists that fit in one batch (a list holds at most VQ_CAP <= SEL_BATCH keys)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (off[mid] - base <= SEL_BATCH) lo = mid; else hi = mid - 1;
+        }
+        const int lb = lo, n = off[lb] - base;
+        // which list does element e of the batch come from?  one lane per list writes its id over the list's span
+        // (shared-memory stores only), so that the global loads below are independent and all in flight at once
+        for (int l = la + lane; l < lb; l += 32) {
+            const int e0 = off[l] - base, e1 = off[l + 1] - base;
+            for (int e = e0; e < e1; e++) owner[e] = (uint16_t)l;
+        }
+        __syncwarp();
+        uint64_t key[SEL_R];
+#pragma unroll
+        for (int r = 0; r < SEL_R; r++) {
+            const int e = r * 32 + lane;
+            key[r] = 0ull;
+            if (e < n) {
+                const int l = owner[e];
+                const int set = l == 0 ? 0 : set_begin + l - 1;
+                key[r] = __ldcg(reinterpret_cast<const unsigned long long*>(lists + ((size_t)set * nq_pad + q) * VQ_CAP) + (base + e - off[l]));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SEL_R; r++) key[r] = (r * 32 + lane) < n ? raw_to_key(key[r]) : 0ull;
+        __syncwarp();
+        uint64_t top[4];
+        warp_select_top128<SEL_R>(key, top, slots + 256, lane);
+        merge_top128(run, top, lane);
+        la = lb;
+    }
+    const int have = total < k ? total : k;
+    uint64_t* dst = lists + (size_t)q * VQ_CAP;  // set 0
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = r * 32 + lane;
+        if (e < have) dst[e] = key_to_raw(run[r]);
+        // the next pass samples rows with LOWER ids too, so a score equal to the k-th must still pass its strict
+        // compare: hand out the next float below the k-th score
+        if (e == k - 1 && thr_out) thr_out[q] = total >= k ? next_below(key_score(run[r])) : -FLT_MAX;
+        if (out_scores && e < k) {
+            out_scores[(size_t)q * k + e] = e < have ? key_score(run[r]) : -FLT_MAX;
+            out_ids[(size_t)q * k + e] = e < have ? (long long)key_row(run[r]) + id_offset : -1;
+        }
+    }
+    if (lane == 0) counts[q] = have;
+}
+
 // Cross-GPU merge: per query, the G per-shard top-k lists [n_lists][nq][k_in] -> global top-k_out.
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long stride_s, long long stride_i, int n_lists,
@@ -333,6 +436,26 @@ int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin
                        float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream) {
     if (nq <= 0) return 0;
     if (n_sets + 1 > MERGE_MAX_SETS) return -2;
+    static int impl_sort = -1;
+    if (impl_sort < 0) {
+        const char* e = getenv("VQ_MERGE_IMPL");
+        impl_sort = (e && e[0] == 's') ? 1 : 0;
+    }
+    if (!impl_sort) {
+        const size_t smem = (size_t)SEL_WARPS * (256 + 128) * sizeof(uint64_t);  // 12 KB
+        static bool attr_sel[64] = {};
+        int dev_s = 0;
+        cudaGetDevice(&dev_s);
+        if (!attr_sel[dev_s & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(merge_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return -(int)e;
+            attr_sel[dev_s & 63] = true;
+        }
+        merge_select_kernel<<<(nq + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, smem, stream>>>(lists, counts, use_set0, set_begin, n_sets, nq_pad, nq, k,
+                                                                                              id_offset, thr_out, out_scores, out_ids);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : -(int)e;
+    }
     // capacity: at least one full list + the running top-k must fit (larger totals take several gather rounds)
     const int cap = pick_cap(expected_total, VQ_CAP);
     // 256-thread CTAs: 8 resident per SM (1,184 on 148 SMs).  More queries than that would leave a second, nearly empty

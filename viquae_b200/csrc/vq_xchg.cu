@@ -116,72 +116,65 @@ __device__ __forceinline__ void merge_top128(uint64_t (&a)[4], const uint64_t (&
     }
 }
 
-// One CTA per query: wait for the flags, pull the query's k_in entries of every rank's published list from the
-// peers' slots (scores f32 [nq, k_in] then ids i64 [nq, k_in] at ids_off), merge to the global top k_out.
-// T threads per CTA: 256, or 128 when that keeps all queries in one wave (see merge_lists_launch).
-template <int T>
-__global__ void __launch_bounds__(T)
+constexpr int PM_WARPS = 4;             // queries per CTA (one warp each)
+constexpr int PM_R = 32;
+constexpr int PM_BATCH = 32 * PM_R;     // keys per selection batch
+
+// One WARP per query (4 per CTA): the CTA waits for the flags, then every warp pulls its query's k_in entries of every
+// rank's published list straight from the peers' slots (scores f32 [nq, k_in] then ids i64 [nq, k_in] at ids_off),
+// whole lists at a time in batches of <= 1024 keys, selects each batch's top 128 (warp_select_top128) and folds it
+// into the running top-128 -> global top k_out.
+__global__ void __launch_bounds__(PM_WARPS * 32)
 pull_merge_kernel(const XchgControl* ctl, XchgPeers peers, size_t slot_bytes, size_t ids_off, int world, int nq, int k_in, int k_out,
                   float* __restrict__ out_scores, long long* __restrict__ out_ids) {
-    constexpr int MERGE_THREADS = T, MERGE_WARPS = T / 32;
-    extern __shared__ uint64_t keys[];  // [cap] gathered keys, reused as [WARPS][128] by the tree
-    const int q = blockIdx.x;
+    extern __shared__ uint64_t pm_smem[];  // per warp: [PM_BATCH] staging + [128] slots
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * PM_WARPS + warp;
     const unsigned want = ctl->seq;  // this rank published `want` earlier on this stream
-    if (!wait_all(ctl, world, want)) {
-        for (int e = threadIdx.x; e < k_out; e += MERGE_THREADS) {
+    const bool arrived = wait_all(ctl, world, want);
+    if (q >= nq) return;
+    if (!arrived) {
+        for (int e = lane; e < k_out; e += 32) {
             out_scores[(size_t)q * k_out + e] = -FLT_MAX;
             out_ids[(size_t)q * k_out + e] = -2;  // poisoned: a peer never arrived
         }
         return;
     }
+    uint64_t* stage = pm_smem + (size_t)warp * (PM_BATCH + 128);
+    uint64_t* slots = stage + PM_BATCH;
     const size_t par = (size_t)(want & 1u) * slot_bytes;
-    const int n = world * k_in;
-    for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
-        const int c = i / k_in, j = i - c * k_in;
-        const uint8_t* base = peers.slots[c] + par;
-        const size_t at = (size_t)q * k_in + j;
-        const long long id = (long long)ld_volatile_u64(base + ids_off + at * 8);
-        const float s = __uint_as_float(ld_volatile_u32(base + at * 4));
-        keys[i] = id >= 0 ? make_key(s, (uint32_t)id) : 0ull;  // padding sorts last
-    }
-    __syncthreads();
+    const int per = PM_BATCH / k_in;  // whole lists per batch (k_in <= 128 -> >= 8)
     uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
-    for (int c0 = warp * 256; c0 < n; c0 += MERGE_WARPS * 256) {
-        uint64_t ch[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int e = c0 + r * 32 + lane;
-            ch[r] = e < n ? keys[e] : 0ull;
+    for (int c0 = 0; c0 < world; c0 += per) {
+        const int c1 = min(world, c0 + per);
+        const int n = (c1 - c0) * k_in;
+        for (int i = lane; i < n; i += 32) {
+            const int c = c0 + i / k_in, j = i - (i / k_in) * k_in;
+            const uint8_t* base = peers.slots[c] + par;
+            const size_t at = (size_t)q * k_in + j;
+            const long long id = (long long)ld_volatile_u64(base + ids_off + at * 8);
+            const float sc = __uint_as_float(ld_volatile_u32(base + at * 4));
+            stage[i] = id >= 0 ? make_key(sc, (uint32_t)id) : 0ull;  // padding sorts last
         }
-        warp_bitonic_sort_desc<8>(ch, lane);
-        const uint64_t top[4] = {ch[0], ch[1], ch[2], ch[3]};
+        __syncwarp();
+        uint64_t key[PM_R];
+#pragma unroll
+        for (int r = 0; r < PM_R; r++) {
+            const int e = r * 32 + lane;
+            key[r] = e < n ? stage[e] : 0ull;
+        }
+        __syncwarp();
+        uint64_t top[4];
+        warp_select_top128<PM_R>(key, top, slots, lane);
         merge_top128(run, top, lane);
     }
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; r++) keys[warp * 128 + r * 32 + lane] = run[r];
-    __syncthreads();
-    for (int step = 1; step < MERGE_WARPS; step <<= 1) {
-        if ((warp & (2 * step - 1)) == 0) {
-            uint64_t other[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) other[r] = keys[(warp + step) * 128 + r * 32 + lane];
-            merge_top128(run, other, lane);
-#pragma unroll
-            for (int r = 0; r < 4; r++) keys[warp * 128 + r * 32 + lane] = run[r];
-        }
-        __syncthreads();
-    }
-    if (warp == 0) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int e = r * 32 + lane;
-            if (e < k_out) {
-                const bool valid = run[r] != 0ull;
-                out_scores[(size_t)q * k_out + e] = valid ? key_score(run[r]) : -FLT_MAX;
-                out_ids[(size_t)q * k_out + e] = valid ? (long long)key_row(run[r]) : -1;
-            }
+    for (int r = 0; r < 4; r++) {
+        const int e = r * 32 + lane;
+        if (e < k_out) {
+            const bool valid = run[r] != 0ull;
+            out_scores[(size_t)q * k_out + e] = valid ? key_score(run[r]) : -FLT_MAX;
+            out_ids[(size_t)q * k_out + e] = valid ? (long long)key_row(run[r]) : -1;
         }
     }
 }
@@ -214,32 +207,24 @@ int xchg_publish_launch(XchgControl* ctl, uint8_t* slots, size_t slot_bytes, con
     return e == cudaSuccess ? 0 : -(int)e;
 }
 
-template <int T>
-static int xchg_merge_launch_t(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, size_t ids_off, int cap, int world, int nq, int k_in,
-                               int k_out, float* out_scores, long long* out_ids, cudaStream_t stream) {
+int xchg_merge_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, int world, int nq, int k_in, int k_out,
+                      float* out_scores, long long* out_ids, cudaStream_t stream) {
+    if (nq <= 0) return 0;
+    if (k_in < 1 || k_in > VQ_KMAX || k_out < 1 || k_out > VQ_KMAX) return -2;
+    const size_t ids_off = ((size_t)nq * k_in * 4 + 7) / 8 * 8;
+    const size_t smem = (size_t)xchg::PM_WARPS * (xchg::PM_BATCH + 128) * sizeof(uint64_t);  // 36 KB
     static bool attr_set_dev[64] = {};
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set_dev[dev_ & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(xchg::pull_merge_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+        cudaError_t e = cudaFuncSetAttribute(xchg::pull_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return -(int)e;
         attr_set_dev[dev_ & 63] = true;
     }
-    xchg::pull_merge_kernel<T><<<nq, T, (size_t)cap * 8, stream>>>(ctl, peers, slot_bytes, ids_off, world, nq, k_in, k_out, out_scores, out_ids);
+    xchg::pull_merge_kernel<<<(nq + xchg::PM_WARPS - 1) / xchg::PM_WARPS, xchg::PM_WARPS * 32, smem, stream>>>(ctl, peers, slot_bytes, ids_off, world, nq, k_in,
+                                                                                                             k_out, out_scores, out_ids);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
-}
-
-int xchg_merge_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, int world, int nq, int k_in, int k_out,
-                      float* out_scores, long long* out_ids, cudaStream_t stream) {
-    if (nq <= 0) return 0;
-    if (k_in < 1 || k_out < 1 || k_out > VQ_KMAX || (long long)world * k_in > 8192) return -2;
-    int cap = 1024;
-    while (cap < world * k_in) cap <<= 1;
-    const size_t ids_off = ((size_t)nq * k_in * 4 + 7) / 8 * 8;
-    if (nq > 1184 && nq <= 2368 && cap <= 2048)
-        return xchg_merge_launch_t<128>(ctl, peers, slot_bytes, ids_off, cap, world, nq, k_in, k_out, out_scores, out_ids, stream);
-    return xchg_merge_launch_t<256>(ctl, peers, slot_bytes, ids_off, cap, world, nq, k_in, k_out, out_scores, out_ids, stream);
 }
 
 int xchg_gather_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slot_bytes, int world, size_t bytes, void* dst, cudaStream_t stream) {
