@@ -608,6 +608,12 @@ def run_latency_config(args, ctx):
             call()
         ctx.barrier()
         lat = []
+        # kernels per call: one direct (uncaptured) call counted by the engine + publish and pull-merge when sharded
+        from viquae_b200 import _lib as _vl
+        n0 = int(_vl.load().vq_index_launch_count(index._h))
+        (sharded.search_tensors(q, k) if sharded is not None else index.search_tensors(q, k))
+        launches_per_call = int(_vl.load().vq_index_launch_count(index._h)) - n0 + (2 if sharded is not None else 0)
+        ctx.barrier()
         for _ in range(args.steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -653,7 +659,7 @@ def run_latency_config(args, ctx):
                         "hbm_floor_us_per_shard": round(floor_us, 1)},
             "e2e": {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4, "d2h_bytes_per_step": nq * k * 12,
                     "ms_per_step": e2e_ms, "what": f"host-buffer call at nq={nq}"},
-            "gpu_launches": None,
+            "gpu_launches": launches_per_call * args.steps,
             "roofline": {"bound": "hbm", "achieved": (r1 - r0) * args.dim * 2 / (last["p50_us"] * 1e-6) / 1e9, "peak": hbm / 1e9, "unit": "GB/s",
                          "frac": last["hbm_frac_p50"], "traffic": None, "kernel": "tc_topk_kernel<1>",
                          "note": "whole call (all passes + merges + exchange) against the shard's HBM stream time"},
@@ -739,10 +745,17 @@ def run_fusion_config(args, ctx):
         fs, fi, fc = pipeline(*qs)
         return fs.cpu(), fi.cpu(), fc.cpu()
 
+    from viquae_b200 import _lib as _vl
+    _count = lambda: sum(int(_vl.load().vq_index_launch_count(ix._h)) for ix in (text, image, face))  # noqa: E731
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
     time.sleep(0.3)
-    total_ms, t0, t1 = ctx.timed(step_device, args.steps, args.warmup)
+    for _ in range(args.warmup):
+        step_device()
+    n0 = _count()
+    total_ms, t0, t1 = ctx.timed(step_device, args.steps, 0)
+    # the three searches (counted by the engine) + 3 expand_hits + union / gstats x2 / combine per step
+    launches = _count() - n0 + args.steps * (3 + 4)
     clocks = sampler.stop(t0, t1)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(5)]
     for e in evs:
@@ -770,7 +783,7 @@ def run_fusion_config(args, ctx):
         "e2e": {"value": nq / (e2e_ms / args.steps / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in q_hosts)), "d2h_bytes_per_step": int(fs.numel() * 8 + fi.numel() * 8 + fc.numel() * 4),
                 "what": "host f32 queries of the three indexes in, host fused run (scores f64, ids i64, counts) out"},
-        "gpu_launches": None,
+        "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                      "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "tc_topk_kernel (three searches) + expand_hits + fuse",
                      "peak_source": src, "note": "whole pipeline time against the three contractions' flops"},

@@ -570,6 +570,38 @@ def test_cuda_graph_replay_equals_direct_search():
         cap.replay()
 
 
+def test_chained_small_batch_launches_equal_the_large_batch_path():
+    """Batches of <= 128 queries chain their kernels with programmatic dependent launches (the next pass's contraction
+    starts streaming while the previous pass's merge still runs; only its epilogue waits).  Many back-to-back calls of
+    varying size, never synchronised in between, must return exactly what the CTA-pair path (plain launches) returns
+    for the same queries: scores are the same TMEM accumulations and ties break by id on both paths."""
+    from viquae_b200.index import B200FlatIndex
+    X, Q = make(300000, 200, 128, "bf16", seed=41)
+    idx = B200FlatIndex(d=128, dtype="bf16")
+    idx.add(torch.from_numpy(X).cuda())
+    Qd = torch.from_numpy(Q).cuda()
+    s_ref, i_ref = idx.search_tensors(Qd, 100)          # 200 queries -> cta_group::2, no chaining
+    outs = []
+    rng = np.random.default_rng(0)
+    for it in range(60):
+        n = int(rng.choice([1, 2, 5, 8, 31, 32, 64, 128]))
+        a = int(rng.integers(0, 200 - n + 1))
+        outs.append((a, n, idx.search_tensors(Qd[a:a + n].contiguous(), 100)))
+    torch.cuda.synchronize()
+    for a, n, (s, i) in outs:
+        assert torch.equal(i, i_ref[a:a + n]) and torch.equal(s, s_ref[a:a + n]), (a, n)
+    # and through a CUDA graph, replayed back to back
+    cap = idx.capture_search(5, 100, query_dtype=Qd.dtype)
+    res = []
+    for a in (0, 50, 100, 150, 195):
+        s, i = cap(Qd[a:a + 5])
+        res.append((a, s.clone(), i.clone()))
+    torch.cuda.synchronize()
+    for a, s, i in res:
+        assert torch.equal(i, i_ref[a:a + 5]) and torch.equal(s, s_ref[a:a + 5]), a
+    idx.close()
+
+
 REL_TOL_F32X3 = 1e-5  # north star for the fp32 mode: scores within 1e-5 relative of the fp32 reference (measured: <= 3.3e-6, typically 6e-7)
 
 

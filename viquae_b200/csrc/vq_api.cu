@@ -536,15 +536,23 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
         rc = vq::merge_lists_launch(lists, counts, 0, 1, sp.pass_sets, sp.nq_pad, nq, k, id_offset, nullptr, out_scores, out_ids, 512, s);
         idx->launches += 1;
     } else if (sp.kind == 1) {
+        // Latency regime (one query tile, one CTA per SM, a handful of merge CTAs): chain the kernels of a search with
+        // programmatic dependent launches — the merge of pass p becomes resident while the contraction runs, and the
+        // contraction of pass p+1 starts streaming tiles while that merge runs (only its epilogue waits for the
+        // thresholds).  Needs every merge CTA resident at once (they wait inside the kernel): few queries only.
+        static int no_pdl = -1;
+        if (no_pdl < 0) no_pdl = getenv("VQ_NO_PDL") ? 1 : 0;
+        const bool pdl = !no_pdl && sp.tc[0].cg == 1 && nq <= 128;
         for (int p = 0; p < sp.n_passes && !rc; p++) {
             const bool last = p == sp.n_passes - 1;
-            vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, 1, ub_score, ub_row};
+            vq::TcPass pass = {sp.tile_b[p], sp.tile_b[p + 1], 1, sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, 1, ub_score, ub_row,
+                               pdl ? (p ? 2 : 1) : 0};
             rc = vq::tc_topk_launch(qprep, nq, idx->ld, idx->data, ntot, idx->ld, idx->kd, idx->kdtype, k, sp.tc[p], pass, lists, counts, progress, s);
             // first pass: every row is a candidate; primed passes add ~ratio * k candidates per query
             const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 256 + k : ((sp.ratio + 2) * k > 2048 ? (sp.ratio + 2) * k : 2048);  // ~ (ratio + 1) * k; more takes gather rounds
             if (!rc)
                 rc = vq::merge_lists_launch(lists, counts, p > 0, 1, sp.tc[p].list_sets, sp.nq_pad, nq, k, id_offset, last ? nullptr : thr,
-                                            last ? out_scores : nullptr, last ? out_ids : nullptr, expected, s);
+                                            last ? out_scores : nullptr, last ? out_ids : nullptr, expected, s, pdl ? 1 : 0);
             idx->launches += 2;
         }
     } else if (sp.kind == 0) {

@@ -23,6 +23,13 @@
 
 namespace vq {
 
+// Programmatic dependent launch (PTX griddepcontrol).  launch_dependents: kernels queued behind this one with the
+// programmatic-stream-serialization attribute may start as soon as every CTA of this grid has executed it (or exited).
+// wait: blocks until the kernels this grid depends on have completed and their writes are visible; a no-op for a
+// kernel that was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t f2ord(float f) {
     uint32_t u = __float_as_uint(f);
     return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);

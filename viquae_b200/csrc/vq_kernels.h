@@ -58,6 +58,8 @@ struct TcParams {
     const float* ub_score;
     const uint32_t* ub_row;
     uint32_t idesc_base;
+    int pdl;              // programmatic dependent launch: trigger the dependents at the start; only the EPILOGUE waits for the
+                          // preceding kernel (the merge that produces init_thr) — producer and MMA warps run ahead
 };
 // one pass over corpus tiles [tile_begin, tile_end): plan must come from tc_plan(nq, (tile_end - tile_begin) * 256 rows)
 struct TcPass {
@@ -67,6 +69,8 @@ struct TcPass {
     int init_thr_stride;
     const float* ub_score;
     const uint32_t* ub_row;
+    int pdl;   // 0 = plain launch; 1 = kernel triggers its dependents early, launched plainly itself (first pass);
+               // 2 = also launched with programmatic stream serialization (its epilogue waits for the preceding merge)
 };
 void tc_plan(int nq, long long n_rows, int n_sms, int force_cg, TcPlan* plan);
 int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long n_rows, int ld_x, int d, int dtype, int k,
@@ -87,8 +91,10 @@ int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long 
 // the RUNNING merged top-k of all passes so far.  Gathers set 0 (if use_set0) + sets [set_begin, set_begin+n_sets),
 // keeps the best k in set 0, writes every query's k-th score to thr_out (may be null) and, if out_scores is
 // given, the final [nq][k] scores (f32) / ids (i64, + id_offset).  expected_total sizes the shared-memory sort.
+// pdl != 0: launched with programmatic stream serialization (the kernel triggers ITS dependents at once and waits for the
+// preceding contraction kernel itself) — only for grids that are fully resident at once (few queries)
 int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
-                       float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream);
+                       float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream, int pdl = 0);
 // banded rounds (k > 128): copies one round's [nq][kr] result into columns [col0, col0+kr) of the final [nq][k]
 // outputs (+ id_offset) and sets the next round's exclusive upper bound to the round's last entry
 int band_scatter_launch(const float* tmp_s, const long long* tmp_i, int nq, int kr, int k, int col0, long long id_offset,

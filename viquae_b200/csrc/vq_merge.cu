@@ -1,4 +1,5 @@
-// K4 — k-way merges of sorted candidate lists, one CTA per query, bitonic sort in shared memory.
+// K4 — k-way merges of candidate lists, one warp per query: selection of the top 128 (bitwise search for the 128-th key,
+// ballot compaction, one 128-key register sort) instead of sorting everything.
 //
 //  * merge_lists: folds the per-(corpus slab, query) candidate-key lists written by K1/K2/K3 into
 //    the final [nq, k] (scores, ids) the reference returns from faiss_index.search
@@ -56,163 +57,14 @@ __device__ __forceinline__ void merge_top128(uint64_t (&a)[4], const uint64_t (&
     }
 }
 
-// folds `n` keys at keys[0..n) into the warp's running top-128: warp w takes the 256-key chunks w, w+WARPS, ...
-template <int WARPS = MERGE_WARPS>
-__device__ __forceinline__ void fold_chunks(const uint64_t* keys, int n, uint64_t (&run)[4], int warp, int lane) {
-    for (int c0 = warp * 256; c0 < n; c0 += WARPS * 256) {
-        uint64_t ch[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int e = c0 + r * 32 + lane;
-            ch[r] = e < n ? keys[e] : 0ull;
-        }
-        warp_bitonic_sort_desc<8>(ch, lane);
-        const uint64_t top[4] = {ch[0], ch[1], ch[2], ch[3]};
-        merge_top128(run, top, lane);
-    }
-}
-
-// WARPS per-warp top-128 sets -> warp 0 holds the CTA-wide top-128 (sorted).  wtop: [WARPS][128] keys of shared memory.
-template <int WARPS = MERGE_WARPS>
-__device__ __forceinline__ void tree_merge(uint64_t* wtop, uint64_t (&run)[4], int warp, int lane) {
-#pragma unroll
-    for (int r = 0; r < 4; r++) wtop[warp * 128 + r * 32 + lane] = run[r];
-    __syncthreads();
-    for (int step = 1; step < WARPS; step <<= 1) {
-        if ((warp & (2 * step - 1)) == 0) {
-            uint64_t other[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) other[r] = wtop[(warp + step) * 128 + r * 32 + lane];
-            merge_top128(run, other, lane);
-#pragma unroll
-            for (int r = 0; r < 4; r++) wtop[warp * 128 + r * 32 + lane] = run[r];
-        }
-        __syncthreads();
-    }
-}
-
-// Merge step of one pass, one CTA per query.  Gathers the (unsorted) candidate lists — the running merged list
-// in set 0 (if use_set0) plus sets [set_begin, set_begin + n_sets) — into shared memory; every warp sorts
-// 256-key chunks in registers and keeps a running top-128; a 3-level tree leaves the CTA-wide top-128 in
-// warp 0, which writes the best k back to set 0 (sorted raw pairs + count), the k-th score to thr_out (the
-// primed threshold of the next pass) and, for the last pass, the final (scores, ids).
-// T threads per CTA: 256 (lowest latency per query) or 128 (twice as many CTAs resident: one wave at 1,250 queries,
-// where 256-thread CTAs need a second, almost empty wave)
-template <int T>
-__global__ void __launch_bounds__(T)
-merge_lists_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int use_set0, int set_begin, int n_sets, int nq_pad, int k,
-                   long long id_offset, float* __restrict__ thr_out, float* __restrict__ out_scores, long long* __restrict__ out_ids,
-                   int cap) {
-    constexpr int MERGE_THREADS = T, MERGE_WARPS = T / 32;
-    extern __shared__ uint64_t keys[];           // [cap] gathered keys, then [WARPS][128] for the tree
-    __shared__ int off_s[MERGE_MAX_SETS + 2];     // exclusive prefix sums of the list lengths (index 0 = set 0)
-    __shared__ int warp_tot[MERGE_WARPS];
-    __shared__ int round_end;
-    const int q = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int L = n_sets + 1;  // logical list l: 0 = running merged list (set 0), l >= 1 = set_begin + l - 1
-    // exclusive prefix sums of the list lengths, in parallel: thread t owns lists [t*PER, t*PER + PER)
-    constexpr int PER = (MERGE_MAX_SETS + MERGE_THREADS) / MERGE_THREADS;
-    {
-        int c[PER], mine = 0;
-#pragma unroll
-        for (int j = 0; j < PER; j++) {
-            const int l = threadIdx.x * PER + j;
-            const int set = l == 0 ? 0 : set_begin + l - 1;
-            c[j] = (l >= L || (l == 0 && !use_set0)) ? 0 : __ldcg(counts + (size_t)set * nq_pad + q);
-        }
-#pragma unroll
-        for (int j = 0; j < PER; j++) mine += c[j];
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(VQ_FULL_MASK, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        int before = incl - mine;
-#pragma unroll
-        for (int w = 0; w < MERGE_WARPS; w++) before += w < warp ? warp_tot[w] : 0;
-#pragma unroll
-        for (int j = 0; j < PER; j++) {
-            const int l = threadIdx.x * PER + j;
-            if (l <= L) off_s[l] = before;
-            before += c[j];
-        }
-    }
-    __syncthreads();
-    const int total = off_s[L];
-    uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
-    int l0 = 0;
-    while (l0 < L) {
-        int l1 = L;
-        if (total > cap) {  // several rounds: as many whole lists as fit in the gather buffer
-            if (threadIdx.x == 0) {
-                int e = l0;
-                while (e < L && off_s[e + 1] - off_s[l0] <= cap) e++;
-                round_end = e;
-            }
-            __syncthreads();
-            l1 = round_end;
-        }
-        const int base = off_s[l0];
-        const int n_round = off_s[l1] - base;
-        // flat gather: element i of the round lives in the list l with off_s[l] <= base + i < off_s[l + 1]; four
-        // independent loads in flight per thread (this kernel is latency-bound at small query counts)
-        for (int i0 = threadIdx.x; i0 < n_round; i0 += 4 * MERGE_THREADS) {
-            unsigned long long raw[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * MERGE_THREADS;
-                raw[u] = 0ull;
-                if (i < n_round) {
-                    const int x = base + i;
-                    int lo = l0, hi = l1;  // invariant: off_s[lo] <= x < off_s[hi]
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (off_s[mid] <= x) lo = mid; else hi = mid;
-                    }
-                    const int set = lo == 0 ? 0 : set_begin + lo - 1;
-                    raw[u] = __ldcg(reinterpret_cast<const unsigned long long*>(lists + ((size_t)set * nq_pad + q) * VQ_CAP) + (x - off_s[lo]));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + u * MERGE_THREADS;
-                if (i < n_round) keys[i] = raw_to_key(raw[u]);
-            }
-        }
-        __syncthreads();
-        fold_chunks<MERGE_WARPS>(keys, n_round, run, warp, lane);
-        __syncthreads();
-        l0 = l1;
-    }
-    tree_merge<MERGE_WARPS>(keys, run, warp, lane);
-    if (warp == 0) {
-        const int have = total < k ? total : k;
-        uint64_t* dst = lists + (size_t)q * VQ_CAP;  // set 0
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int e = r * 32 + lane;
-            if (e < have) dst[e] = key_to_raw(run[r]);
-            // the next pass samples rows with LOWER ids too, so a score equal to the k-th must still pass its
-            // strict compare: hand out the next float below the k-th score
-            if (e == k - 1 && thr_out) thr_out[q] = total >= k ? next_below(key_score(run[r])) : -FLT_MAX;
-            if (out_scores && e < k) {
-                out_scores[(size_t)q * k + e] = e < have ? key_score(run[r]) : -FLT_MAX;
-                out_ids[(size_t)q * k + e] = e < have ? (long long)key_row(run[r]) + id_offset : -1;
-            }
-        }
-        if (lane == 0) counts[q] = have;
-    }
-}
-
-
-// ---- merge step of one pass by SELECTION, one WARP per query (the default; merge_lists_kernel is the sort-everything
-// restatement kept for A/B runs, VQ_MERGE_IMPL=sort).  Same contract as merge_lists_kernel.  The candidates are
-// taken in batches of whole lists (<= 1024 keys, 32 per lane); every batch is reduced to its top 128 by
-// warp_select_top128 and folded into the running top-128.  No block-level barrier: the warps of a CTA are independent.
+// ---- Merge step of one pass, one WARP per query, by SELECTION.  Candidate lists are [set][nq_pad][VQ_CAP] raw pairs +
+// counts[set][nq_pad]; set 0 is the RUNNING merged top-k of all passes so far.  Takes set 0 (if use_set0) + sets
+// [set_begin, set_begin + n_sets) in batches of whole lists (<= 1024 keys, 32 per lane), reduces every batch to its top 128
+// (warp_select_top128: bitwise search for the 128-th key + one 128-key sort) and folds it into the running top-128; writes
+// the best k back to set 0 (sorted raw pairs + count), the k-th score to thr_out (the primed threshold of the next pass)
+// and, for the last pass, the final (scores, ids).  No block-level barrier: the warps of a CTA are independent.
+// (Round 1/early round 2 sorted every 256-key chunk in registers: 20.6 K instructions per query, ALU-pipe bound at 73 %;
+// selection needs ~1/5 of that: 50 -> 27 us per merge at 1,250 queries, 123 -> 74 us for the unprimed pass.)
 constexpr int SEL_R = 32;
 constexpr int SEL_BATCH = 32 * SEL_R;
 constexpr int SEL_WARPS = 4;
@@ -223,6 +75,10 @@ merge_select_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int 
     extern __shared__ uint64_t sel_smem[];                       // per warp: owner ids (u16 [SEL_BATCH] = 256 u64) + [128] slots
     __shared__ int off_all[SEL_WARPS][MERGE_MAX_SETS + 2];        // exclusive prefix sums of the list lengths
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // programmatic dependent launch (no-ops on a plain launch): the next pass's contraction may become resident and stream
+    // its first tiles while this merge runs (its epilogue waits for us); we wait for the contraction that filled the lists
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
     const int q = blockIdx.x * SEL_WARPS + warp;
     if (q >= nq) return;
     uint64_t* slots = sel_smem + (size_t)warp * (256 + 128);
@@ -311,38 +167,52 @@ merge_select_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int 
     if (lane == 0) counts[q] = have;
 }
 
-// Cross-GPU merge: per query, the G per-shard top-k lists [n_lists][nq][k_in] -> global top-k_out.
-__global__ void __launch_bounds__(MERGE_THREADS)
+// Cross-GPU merge (NCCL transport; the peer-memory transport fuses it with the exchange, vq_xchg.cu): per query, the G
+// per-shard top-k lists [n_lists][nq][k_in] -> global top-k_out, one warp per query, whole lists in batches of <= 1024
+// keys reduced by selection (warp_select_top128).
+__global__ void __launch_bounds__(SEL_WARPS * 32)
 merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long stride_s, long long stride_i, int n_lists,
-                  int nq, int k_in, int k_out, float* __restrict__ out_scores, long long* __restrict__ out_ids, int cap) {
-    extern __shared__ uint64_t keys[];
-    const int q = blockIdx.x;
+                  int nq, int k_in, int k_out, float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+    extern __shared__ uint64_t mt_smem[];  // per warp: [SEL_BATCH] staging + [128] slots
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * SEL_WARPS + warp;
+    if (q >= nq) return;
+    uint64_t* stage = mt_smem + (size_t)warp * (SEL_BATCH + 128);
+    uint64_t* slots = stage + SEL_BATCH;
+    const int per = k_in <= SEL_BATCH ? SEL_BATCH / k_in : 1;  // whole lists per batch
     uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
-    const int per_round = cap / k_in;  // whole lists per gather round (>= 1 by construction of cap)
-    for (int c0 = 0; c0 < n_lists; c0 += per_round) {
-        const int c1 = min(n_lists, c0 + per_round);
-        const int n = (c1 - c0) * k_in;
-        for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
-            const int c = c0 + i / k_in, j = i - (i / k_in) * k_in;
-            const size_t at = (size_t)q * k_in + j;  // list c starts stride_s / stride_i elements after list c-1
-            const long long id = ids[(size_t)c * stride_i + at];
-            keys[i] = id >= 0 ? make_key(scores[(size_t)c * stride_s + at], (uint32_t)id) : 0ull;  // padding sorts last
-        }
-        __syncthreads();
-        fold_chunks(keys, n, run, warp, lane);
-        __syncthreads();
-    }
-    tree_merge(keys, run, warp, lane);
-    if (warp == 0) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int e = r * 32 + lane;
-            if (e < k_out) {
-                const bool valid = run[r] != 0ull;
-                out_scores[(size_t)q * k_out + e] = valid ? key_score(run[r]) : -FLT_MAX;
-                out_ids[(size_t)q * k_out + e] = valid ? (long long)key_row(run[r]) : -1;
+    for (int c0 = 0; c0 < n_lists; c0 += per) {
+        const int c1 = min(n_lists, c0 + per);
+        for (int j0 = 0; j0 < k_in; j0 += SEL_BATCH) {  // (a single list longer than a batch is taken in pieces)
+            const int kk = c1 - c0 > 1 ? k_in : min(SEL_BATCH, k_in - j0);
+            const int n = (c1 - c0) * kk;
+            for (int i = lane; i < n; i += 32) {
+                const int c = c0 + i / kk, j = j0 + i - (i / kk) * kk;
+                const size_t at = (size_t)q * k_in + j;  // list c starts stride_s / stride_i elements after list c-1
+                const long long id = ids[(size_t)c * stride_i + at];
+                stage[i] = id >= 0 ? make_key(scores[(size_t)c * stride_s + at], (uint32_t)id) : 0ull;  // padding sorts last
             }
+            __syncwarp();
+            uint64_t key[SEL_R];
+#pragma unroll
+            for (int r = 0; r < SEL_R; r++) {
+                const int e = r * 32 + lane;
+                key[r] = e < n ? stage[e] : 0ull;
+            }
+            __syncwarp();
+            uint64_t top[4];
+            warp_select_top128<SEL_R>(key, top, slots, lane);
+            merge_top128(run, top, lane);
+            if (c1 - c0 > 1) break;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = r * 32 + lane;
+        if (e < k_out) {
+            const bool valid = run[r] != 0ull;
+            out_scores[(size_t)q * k_out + e] = valid ? key_score(run[r]) : -FLT_MAX;
+            out_ids[(size_t)q * k_out + e] = valid ? (long long)key_row(run[r]) : -1;
         }
     }
 }
@@ -407,41 +277,11 @@ merge_topk_big_kernel(const float* __restrict__ scores, const long long* __restr
     }
 }
 
-static int pick_cap(long long total, int k) {
-    long long need = total > 2LL * k ? total : 2LL * k;
-    int cap = 1024;  // also hosts the [8][128] tree buffer
-    while (cap < need && cap < MERGE_CAP_MAX) cap <<= 1;
-    return cap;
-}
-
-template <int T>
-static int merge_lists_launch_t(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
-                                float* thr_out, float* out_scores, long long* out_ids, int cap, cudaStream_t stream) {
-    static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    bool& attr_set = attr_set_dev[dev_ & 63];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(merge_lists_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP_MAX * 8);
-        if (e != cudaSuccess) return -(int)e;
-        attr_set = true;
-    }
-    merge_lists_kernel<T><<<nq, T, (size_t)cap * sizeof(uint64_t), stream>>>(lists, counts, use_set0, set_begin, n_sets, nq_pad, k, id_offset, thr_out,
-                                                                         out_scores, out_ids, cap);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : -(int)e;
-}
-
 int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin, int n_sets, int nq_pad, int nq, int k, long long id_offset,
-                       float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream) {
+                       float* thr_out, float* out_scores, long long* out_ids, int expected_total, cudaStream_t stream, int pdl) {
     if (nq <= 0) return 0;
     if (n_sets + 1 > MERGE_MAX_SETS) return -2;
-    static int impl_sort = -1;
-    if (impl_sort < 0) {
-        const char* e = getenv("VQ_MERGE_IMPL");
-        impl_sort = (e && e[0] == 's') ? 1 : 0;
-    }
-    if (!impl_sort) {
+    {
         const size_t smem = (size_t)SEL_WARPS * (256 + 128) * sizeof(uint64_t);  // 12 KB
         static bool attr_sel[64] = {};
         int dev_s = 0;
@@ -451,23 +291,20 @@ int merge_lists_launch(uint64_t* lists, int* counts, int use_set0, int set_begin
             if (e != cudaSuccess) return -(int)e;
             attr_sel[dev_s & 63] = true;
         }
-        merge_select_kernel<<<(nq + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, smem, stream>>>(lists, counts, use_set0, set_begin, n_sets, nq_pad, nq, k,
-                                                                                              id_offset, thr_out, out_scores, out_ids);
-        cudaError_t e = cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((nq + SEL_WARPS - 1) / SEL_WARPS));
+        cfg.blockDim = dim3(SEL_WARPS * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, merge_select_kernel, lists, counts, use_set0, set_begin, n_sets, nq_pad, nq, k, id_offset, thr_out,
+                                           out_scores, out_ids);
         return e == cudaSuccess ? 0 : -(int)e;
     }
-    // capacity: at least one full list + the running top-k must fit (larger totals take several gather rounds)
-    const int cap = pick_cap(expected_total, VQ_CAP);
-    // 256-thread CTAs: 8 resident per SM (1,184 on 148 SMs).  More queries than that would leave a second, nearly empty
-    // wave: 128-thread CTAs (16 per SM) keep it to one.
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("VQ_MERGE_THREADS");
-        forced = e ? atoi(e) : 0;
-    }
-    const bool small = forced ? forced == 128 : (nq > 1184 && nq <= 2368 && cap <= 2048);
-    if (small) return merge_lists_launch_t<128>(lists, counts, use_set0, set_begin, n_sets, nq_pad, nq, k, id_offset, thr_out, out_scores, out_ids, cap, stream);
-    return merge_lists_launch_t<256>(lists, counts, use_set0, set_begin, n_sets, nq_pad, nq, k, id_offset, thr_out, out_scores, out_ids, cap, stream);
 }
 
 int merge_topk_launch(const float* scores, const long long* ids, long long stride_s, long long stride_i, int n_lists, int nq, int k_in,
@@ -492,18 +329,9 @@ int merge_topk_launch(const float* scores, const long long* ids, long long strid
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : -(int)e;
     }
-    const int cap = pick_cap((long long)n_lists * k_in, k_in > k_out ? k_in : k_out);
-    const size_t smem = (size_t)cap * sizeof(uint64_t);
-    static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    bool& attr_set = attr_set_dev[dev_ & 63];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_CAP_MAX * 8);
-        if (e != cudaSuccess) return -(int)e;
-        attr_set = true;
-    }
-    merge_topk_kernel<<<nq, MERGE_THREADS, smem, stream>>>(scores, ids, stride_s, stride_i, n_lists, nq, k_in, k_out, out_scores, out_ids, cap);
+    const size_t smem = (size_t)SEL_WARPS * (SEL_BATCH + 128) * sizeof(uint64_t);  // 36 KB
+    merge_topk_kernel<<<(nq + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, smem, stream>>>(scores, ids, stride_s, stride_i, n_lists, nq, k_in, k_out,
+                                                                                        out_scores, out_ids);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
 }

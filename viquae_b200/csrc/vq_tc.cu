@@ -298,6 +298,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const int n_clusters = gridDim.x / CG;
 
     if (CG > 1) cluster_sync_all();
+    if (p.pdl && threadIdx.x == 0) pdl_launch_dependents();  // the pass's merge kernel may become resident now (it waits for us)
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_q);
         prefetch_tmap(&tmap_x);
@@ -431,6 +432,11 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const uint32_t lane_field = (uint32_t)(ew * 32) << 16;
         const int k = p.k;
         uint32_t iter = 0;
+        // Programmatic dependent launch: this kernel may have started while the previous pass's merge was still running.
+        // The operands (queries, corpus) were complete long before; what the merge produces — the primed thresholds — and
+        // what it still reads — the candidate lists this epilogue is about to overwrite — are touched only after this wait.
+        // Producer and MMA warps never wait: they stream the first tiles into TMEM meanwhile.
+        if (p.pdl) pdl_wait();
         for (int item = cluster_id; item < n_items; item += n_clusters) {
             const int m_tile = item % p.m_tiles, chunk = item / p.m_tiles;
             const int q = (m_tile * CG + (int)rank) * BLOCK_Q + ew * 32 + lane;  // this thread's query
@@ -538,7 +544,7 @@ static int encode_2d(CUtensorMap* m, const void* base, int dtype, uint64_t rows,
 }
 
 template <int CG>
-static int launch_cg(const CUtensorMap& tq, const CUtensorMap& tx, const TcParams& p, int n_clusters, cudaStream_t stream) {
+static int launch_cg(const CUtensorMap& tq, const CUtensorMap& tx, const TcParams& p, int n_clusters, cudaStream_t stream, bool pdl_launch) {
     using C = Cfg<CG>;
     static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
     int dev_ = 0;
@@ -554,13 +560,18 @@ static int launch_cg(const CUtensorMap& tq, const CUtensorMap& tx, const TcParam
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (pdl_launch) {  // may start before the preceding kernel (the previous pass's merge) has finished
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, tc_topk_kernel<CG>, tq, tx, p);
     return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -660,7 +671,9 @@ int tc_topk_launch(const void* q16, int nq, int ld_q, const void* x16, long long
     // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format bf16 = 1 / f16 = 0 (bits 7-9, 10-12), both K-major
     const uint32_t fmt = (dtype == VQ_DTYPE_BF16) ? 1u : 0u;
     p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10);
-    return plan.cg == 2 ? tc::launch_cg<2>(tq, tx, p, plan.n_clusters, stream) : tc::launch_cg<1>(tq, tx, p, plan.n_clusters, stream);
+    p.pdl = pass.pdl != 0;
+    const bool pdl_launch = pass.pdl == 2;
+    return plan.cg == 2 ? tc::launch_cg<2>(tq, tx, p, plan.n_clusters, stream, pdl_launch) : tc::launch_cg<1>(tq, tx, p, plan.n_clusters, stream, pdl_launch);
 }
 
 }  // namespace vq
