@@ -173,12 +173,11 @@ merge_select_kernel(uint64_t* __restrict__ lists, int* __restrict__ counts, int 
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long stride_s, long long stride_i, int n_lists,
                   int nq, int k_in, int k_out, float* __restrict__ out_scores, long long* __restrict__ out_ids) {
-    extern __shared__ uint64_t mt_smem[];  // per warp: [SEL_BATCH] staging + [128] slots
+    extern __shared__ uint64_t mt_smem[];  // per warp: [128] slots of the selection
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * SEL_WARPS + warp;
     if (q >= nq) return;
-    uint64_t* stage = mt_smem + (size_t)warp * (SEL_BATCH + 128);
-    uint64_t* slots = stage + SEL_BATCH;
+    uint64_t* slots = mt_smem + (size_t)warp * 128;
     const int per = k_in <= SEL_BATCH ? SEL_BATCH / k_in : 1;  // whole lists per batch
     uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
     for (int c0 = 0; c0 < n_lists; c0 += per) {
@@ -186,20 +185,26 @@ merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict_
         for (int j0 = 0; j0 < k_in; j0 += SEL_BATCH) {  // (a single list longer than a batch is taken in pieces)
             const int kk = c1 - c0 > 1 ? k_in : min(SEL_BATCH, k_in - j0);
             const int n = (c1 - c0) * kk;
-            for (int i = lane; i < n; i += 32) {
-                const int c = c0 + i / kk, j = j0 + i - (i / kk) * kk;
-                const size_t at = (size_t)q * k_in + j;  // list c starts stride_s / stride_i elements after list c-1
-                const long long id = ids[(size_t)c * stride_i + at];
-                stage[i] = id >= 0 ? make_key(scores[(size_t)c * stride_s + at], (uint32_t)id) : 0ull;  // padding sorts last
-            }
-            __syncwarp();
+            // all loads of the batch in flight before the first use
             uint64_t key[SEL_R];
+            uint32_t sc[SEL_R];
 #pragma unroll
             for (int r = 0; r < SEL_R; r++) {
                 const int e = r * 32 + lane;
-                key[r] = e < n ? stage[e] : 0ull;
+                key[r] = ~0ull;  // id -1
+                sc[r] = 0u;
+                if (e < n) {
+                    const int c = c0 + e / kk, j = j0 + e - (e / kk) * kk;
+                    const size_t at = (size_t)q * k_in + j;  // list c starts stride_s / stride_i elements after list c-1
+                    key[r] = (uint64_t)ids[(size_t)c * stride_i + at];
+                    sc[r] = __float_as_uint(scores[(size_t)c * stride_s + at]);
+                }
             }
-            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < SEL_R; r++) {
+                const long long id = (long long)key[r];
+                key[r] = id >= 0 ? make_key(__uint_as_float(sc[r]), (uint32_t)id) : 0ull;  // padding sorts last
+            }
             uint64_t top[4];
             warp_select_top128<SEL_R>(key, top, slots, lane);
             merge_top128(run, top, lane);
@@ -329,7 +334,7 @@ int merge_topk_launch(const float* scores, const long long* ids, long long strid
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : -(int)e;
     }
-    const size_t smem = (size_t)SEL_WARPS * (SEL_BATCH + 128) * sizeof(uint64_t);  // 36 KB
+    const size_t smem = (size_t)SEL_WARPS * 128 * sizeof(uint64_t);  // 4 KB
     merge_topk_kernel<<<(nq + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, smem, stream>>>(scores, ids, stride_s, stride_i, n_lists, nq, k_in, k_out,
                                                                                         out_scores, out_ids);
     cudaError_t e = cudaGetLastError();

@@ -127,7 +127,7 @@ constexpr int PM_BATCH = 32 * PM_R;     // keys per selection batch
 __global__ void __launch_bounds__(PM_WARPS * 32)
 pull_merge_kernel(const XchgControl* ctl, XchgPeers peers, size_t slot_bytes, size_t ids_off, int world, int nq, int k_in, int k_out,
                   float* __restrict__ out_scores, long long* __restrict__ out_ids) {
-    extern __shared__ uint64_t pm_smem[];  // per warp: [PM_BATCH] staging + [128] slots
+    extern __shared__ uint64_t pm_smem[];  // per warp: [128] slots of the selection
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * PM_WARPS + warp;
     const unsigned want = ctl->seq;  // this rank published `want` earlier on this stream
@@ -140,30 +140,35 @@ pull_merge_kernel(const XchgControl* ctl, XchgPeers peers, size_t slot_bytes, si
         }
         return;
     }
-    uint64_t* stage = pm_smem + (size_t)warp * (PM_BATCH + 128);
-    uint64_t* slots = stage + PM_BATCH;
+    uint64_t* slots = pm_smem + (size_t)warp * 128;
     const size_t par = (size_t)(want & 1u) * slot_bytes;
     const int per = PM_BATCH / k_in;  // whole lists per batch (k_in <= 128 -> >= 8)
     uint64_t run[4] = {0ull, 0ull, 0ull, 0ull};
     for (int c0 = 0; c0 < world; c0 += per) {
         const int c1 = min(world, c0 + per);
         const int n = (c1 - c0) * k_in;
-        for (int i = lane; i < n; i += 32) {
-            const int c = c0 + i / k_in, j = i - (i / k_in) * k_in;
-            const uint8_t* base = peers.slots[c] + par;
-            const size_t at = (size_t)q * k_in + j;
-            const long long id = (long long)ld_volatile_u64(base + ids_off + at * 8);
-            const float sc = __uint_as_float(ld_volatile_u32(base + at * 4));
-            stage[i] = id >= 0 ? make_key(sc, (uint32_t)id) : 0ull;  // padding sorts last
-        }
-        __syncwarp();
+        // every remote load of the batch is issued before the first one is used: a peer round trip costs ~2-3 us over
+        // NVLink, and a loop that consumes each value before asking for the next would pay it 25 times in a row
         uint64_t key[PM_R];
+        uint32_t sc[PM_R];
 #pragma unroll
         for (int r = 0; r < PM_R; r++) {
             const int e = r * 32 + lane;
-            key[r] = e < n ? stage[e] : 0ull;
+            key[r] = ~0ull;  // id -1
+            sc[r] = 0u;
+            if (e < n) {
+                const int c = c0 + e / k_in, j = e - (e / k_in) * k_in;
+                const uint8_t* base = peers.slots[c] + par;
+                const size_t at = (size_t)q * k_in + j;
+                key[r] = ld_volatile_u64(base + ids_off + at * 8);
+                sc[r] = ld_volatile_u32(base + at * 4);
+            }
         }
-        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < PM_R; r++) {
+            const long long id = (long long)key[r];
+            key[r] = id >= 0 ? make_key(__uint_as_float(sc[r]), (uint32_t)id) : 0ull;  // padding sorts last
+        }
         uint64_t top[4];
         warp_select_top128<PM_R>(key, top, slots, lane);
         merge_top128(run, top, lane);
@@ -212,7 +217,7 @@ int xchg_merge_launch(const XchgControl* ctl, const XchgPeers& peers, size_t slo
     if (nq <= 0) return 0;
     if (k_in < 1 || k_in > VQ_KMAX || k_out < 1 || k_out > VQ_KMAX) return -2;
     const size_t ids_off = ((size_t)nq * k_in * 4 + 7) / 8 * 8;
-    const size_t smem = (size_t)xchg::PM_WARPS * (xchg::PM_BATCH + 128) * sizeof(uint64_t);  // 36 KB
+    const size_t smem = (size_t)xchg::PM_WARPS * 128 * sizeof(uint64_t);  // 4 KB
     static bool attr_set_dev[64] = {};
     int dev_ = 0;
     cudaGetDevice(&dev_);
