@@ -109,6 +109,17 @@ kb = next(iter(sh.kbs.values()))
 assert all(isinstance(e, ShardedB200Index) for e in kb._engines.values()) and len(kb._engines["dpr"]) == n
 s_sh, i_sh = kb.search_batch("dpr", q1, k=k)          # merged result on EVERY rank
 res = kb.dataset.search_batch("clip", q2, k)           # HF entry point -> the sharded engine
+# save_path / load under sharding: every rank writes and reads its own shard file
+shard_path = os.path.join(tmp, "dpr.index")
+kb._engines["dpr"].save(shard_path)
+dist.barrier()
+assert os.path.exists(f"{shard_path}.shard{rank}of{world}")
+cfg_load = config(-1, list(range(world)))
+cfg_load[os.path.join(tmp, "kb")]["index_kwargs"] = {"dpr": {"column": "text_emb", "kind": "B200", "key": "q_text", "string_factory": "Flat",
+                                                              "metric_type": 0, "device": -1, "load": True, "file": shard_path}}
+kb_loaded = KnowledgeBase(os.path.join(tmp, "kb"), **cfg_load[os.path.join(tmp, "kb")])
+s_ld, i_ld = kb_loaded.search_batch("dpr", q1, k=k)
+assert np.array_equal(i_ld, i_sh) and np.array_equal(s_ld, s_sh), "sharded index loaded from its shard files != the one that wrote them"
 if rank == 0:
     one = dataset_search(queries, k=k, metric_save_path=os.path.join(tmp, "metrics_one"), kb_kwargs=config(0, 0),
                          qrels=os.path.join(tmp, "qrels.json"), fusion_kwargs=fusion, map_kwargs={"batch_size": 32})
