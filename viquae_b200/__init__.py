@@ -7,7 +7,8 @@ importing the engine modules without the built library raises.
 """
 __version__ = "0.1.0"
 
-__all__ = ["B200FlatIndex", "ShardedFlatIndex", "KnowledgeBase", "Searcher", "IndexKind", "Index", "Fusion", "Run", "Qrels"]
+__all__ = ["B200FlatIndex", "ShardedFlatIndex", "ShardedB200Index", "KnowledgeBase", "Searcher", "IndexKind", "Index", "Fusion", "Run", "Qrels",
+           "inbatch_step", "mine_hard_negatives"]
 
 
 def __getattr__(name):  # lazy: `import viquae_b200` stays cheap and works where datasets/torch are heavy
@@ -23,6 +24,12 @@ def __getattr__(name):  # lazy: `import viquae_b200` stays cheap and works where
     if name in ("Fusion", "default_minimum", "gzmuv_norm"):
         from . import fuse
         return getattr(fuse, name)
+    if name in ("inbatch_step", "mine_hard_negatives", "gather_global_batch"):
+        from . import inbatch
+        return getattr(inbatch, name)
+    if name in ("ShardedB200Index", "PeerExchange"):
+        from . import sharded
+        return getattr(sharded, name)
     if name in ("Run", "Qrels", "evaluate"):
         from . import runs
         return getattr(runs, name)
