@@ -570,6 +570,30 @@ def test_cuda_graph_replay_equals_direct_search():
         cap.replay()
 
 
+@pytest.mark.parametrize("dtype,nq", [("bf16", 3), ("bf16", 200), ("f32", 40), ("f32x3", 9)])
+def test_massive_exact_ties_resolve_to_the_lowest_ids(dtype, nq):
+    """Every row of the corpus identical (and a second block of identical, slightly better rows in the middle): all scores
+    of a query tie exactly, thousands of tied keys straddle every cut — the primed thresholds (next float below the k-th
+    score), the in-kernel prunes and the selection merges (second bitwise search over the row words) must still return the
+    LOWEST ids, like the oracle's tie rule."""
+    from viquae_b200.index import B200FlatIndex
+    N, d, k = 70000, 64, 100
+    X = np.full((N, d), 0.5, dtype=np.float32)
+    X[30000:30040] = 0.75                      # 40 better rows (all tied among themselves), then 69,960 tied rows
+    Q = np.abs(np.random.default_rng(3).standard_normal((nq, d)).astype(np.float32)) + 0.25
+    if dtype == "bf16":
+        Q = flat_ip.bf16_round(Q)
+    idx = B200FlatIndex(d=d, dtype=dtype)
+    idx.add(X)
+    res = idx.search_batch(Q, k)
+    I = np.asarray(res.total_indices)
+    want = np.concatenate([np.arange(30000, 30040), np.arange(0, k - 40)])
+    assert np.array_equal(I, np.tile(want, (nq, 1))), I[0][:50]
+    D = np.asarray(res.total_scores)
+    assert np.all(D[:, :40] > D[:, 40:41]) and np.all(D[:, 40:] == D[:, 40:41])
+    idx.close()
+
+
 def test_chained_small_batch_launches_equal_the_large_batch_path():
     """Batches of <= 128 queries chain their kernels with programmatic dependent launches (the next pass's contraction
     starts streaming while the previous pass's merge still runs; only its epilogue waits).  Many back-to-back calls of
