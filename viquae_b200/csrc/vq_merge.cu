@@ -1,7 +1,7 @@
 // K4 — k-way merges of candidate lists, one warp per query: selection of the top 128 (bitwise search for the 128-th key,
 // ballot compaction, one 128-key register sort) instead of sorting everything.
 //
-//  * merge_lists: folds the per-(corpus slab, query) candidate-key lists written by K1/K2/K3 into
+//  * merge_lists: folds the per-(corpus slab, query) candidate-key lists written by K1 / K3 into
 //    the final [nq, k] (scores, ids) the reference returns from faiss_index.search
 //    (datasets/search.py:384-385: float32 scores, int64 ids, descending, -1 padding).
 //  * merge_topk: the cross-GPU step — every rank's local top-k [G, nq, k] (after the NCCL
