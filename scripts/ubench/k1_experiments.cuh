@@ -380,7 +380,8 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
         mbar_arrive_expect_tx(&full_bar[p_stage], STAGE_BYTES);
         const uint32_t dst = ring + p_stage * STAGE_BYTES;
         tma_load_2d(&tmap_qt, &full_bar[p_stage], dst, 0, hot ? 0 : pc.qrow + pc.kb * BK);
-        tma_load_2d(&tmap_x, &full_bar[p_stage], dst + A_BYTES, hot ? 0 : pc.kb * BK, hot ? 0 : pc.xrow);
+        if (VAR == 5) tma_load_2d(&tmap_x, &full_bar[p_stage], dst + A_BYTES, 0, hot ? 0 : (pc.xrow / BN) * kpad + pc.kb * BK);
+        else tma_load_2d(&tmap_x, &full_bar[p_stage], dst + A_BYTES, hot ? 0 : pc.kb * BK, hot ? 0 : pc.xrow);
     };
     auto p_next = [&]() {
         if (++p_stage == STAGES) {
@@ -439,7 +440,25 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
                     c_phase ^= 1;
                 }
                 const uint32_t As = ring + s * STAGE_BYTES + a_off, Bs = ring + s * STAGE_BYTES + A_BYTES + b_row;
-                if (VAR == 2) {
+                if (VAR == 5) {
+                    // both operands k-major: queries are the scalars, PAIRS of neighbouring corpus rows the packed operand
+                    // (the inner loop of the register-staged kernel, fed by TMA)
+                    const uint32_t Ak = ring + s * STAGE_BYTES + (uint32_t)ty * 16u, Bk = ring + s * STAGE_BYTES + A_BYTES + (uint32_t)tx * 16u;
+#pragma unroll
+                    for (int kk = 0; kk < BK; kk++) {
+                        const float4 a0 = lds128f(Ak + (uint32_t)kk * 512u);
+                        const float4 a1 = lds128f(Ak + (uint32_t)kk * 512u + 256u);
+                        const ulonglong2 b0 = lds128(Bk + (uint32_t)kk * 512u);
+                        const ulonglong2 b1 = lds128(Bk + (uint32_t)kk * 512u + 256u);
+                        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        const unsigned long long b[4] = {b0.x, b0.y, b1.x, b1.y};
+                        // acc2[p][j] doubles as [pair of rows p][query j]: 4 x 8
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+#pragma unroll
+                            for (int p = 0; p < 4; p++) ffma2(acc2[p][i], a[i], b[p]);
+                    }
+                } else if (VAR == 2) {
                     // corpus operand two k at a time (LDS.64): 16 instead of 32 operand registers
 #pragma unroll
                     for (int c = 0; c < BK / 2; c++) {
@@ -513,8 +532,9 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
                 unsigned long long* list = reinterpret_cast<unsigned long long*>(item_lists + (size_t)r * VQ_CAP);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const long long xr = x0 + tx + 16 * j;
-                    const float s = __uint_as_float((i & 1) ? (uint32_t)(acc2[i >> 1][j] >> 32) : (uint32_t)acc2[i >> 1][j]);
+                    const long long xr = VAR == 5 ? x0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : x0 + tx + 16 * j;
+                    const float s = VAR == 5 ? __uint_as_float((j & 1) ? (uint32_t)(acc2[j >> 1][i] >> 32) : (uint32_t)acc2[j >> 1][i])
+                                             : __uint_as_float((i & 1) ? (uint32_t)(acc2[i >> 1][j] >> 32) : (uint32_t)acc2[i >> 1][j]);
                     if (xr < n_rows && s > thr && (s < ubs || (s == ubs && (uint32_t)xr > ubr))) {
                         const int pos = atomicAdd(&cnt_s[r], 1);
                         __stcg(list + pos, (unsigned long long)pack_raw(s, (uint32_t)xr));
@@ -664,21 +684,25 @@ int f32_topk_tma_launch(const float* qt, int nq, const float* x, long long n_row
     CUtensorMap tq, tx;
     int rc = f32_encode_2d(&tq, qt, (uint64_t)plan.m_tiles * kpad, T::BM, T::BM, T::BM, T::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    rc = f32_encode_2d(&tx, x, (uint64_t)n_rows, (uint64_t)d, (uint64_t)ld_x, T::BK, T::BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    const char* ev = getenv("VQ_F32_TMA_VARIANT");
+    if (ev && atoi(ev) >= 5)  // x is the k-major tiled copy [n_tiles_total][kpad][128] (corpus_kmajor_kernel)
+        rc = f32_encode_2d(&tx, x, (uint64_t)((n_rows + T::BN - 1) / T::BN) * kpad, T::BN, T::BN, T::BN, T::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    else
+        rc = f32_encode_2d(&tx, x, (uint64_t)n_rows, (uint64_t)d, (uint64_t)ld_x, T::BK, T::BN, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     static int var = -1, hot = 0;  // experiment knobs: VQ_F32_TMA_VARIANT picks the instruction arrangement of the inner loop,
                                    // VQ_F32_TMA_HOT=1 makes every load fetch the same tile (wrong results: measurement only)
     if (var < 0) {
         const char* e = getenv("VQ_F32_TMA_VARIANT");
         var = e ? atoi(e) : 0;
-        if (var < 0 || var > 4) var = 0;
+        if (var < 0 || var > 6) var = 0;
         hot = getenv("VQ_F32_TMA_HOT") ? 1 : 0;
     }
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, int, int, long long, int, int, int, int, int, int, int, int, int, int, const float*, const float*,
                            const uint32_t*, uint64_t*, int*);
     kern_t kern = var == 0 ? T::f32_topk_tma_kernel<0, 2> : var == 1 ? T::f32_topk_tma_kernel<1, 2> : var == 2 ? T::f32_topk_tma_kernel<2, 2>
-                : var == 3 ? T::f32_topk_tma_kernel<3, 2> : T::f32_topk_tma_kernel<0, 1>;
-    static bool attr_set_dev[64][5] = {};  // cudaFuncSetAttribute is per device
+                : var == 3 ? T::f32_topk_tma_kernel<3, 2> : var == 4 ? T::f32_topk_tma_kernel<0, 1> : var == 5 ? T::f32_topk_tma_kernel<5, 2> : T::f32_topk_tma_kernel<5, 1>;
+    static bool attr_set_dev[64][7] = {};  // cudaFuncSetAttribute is per device
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set_dev[dev_ & 63][var]) {

@@ -43,6 +43,13 @@ static void run_tma(const char* name, const float* q, int nq, const float* x, lo
     float* qt;
     cudaMalloc(&qt, f32_kmajor_bytes(plan.nq_pad, d));
     f32_queries_kmajor_launch(q, plan.nq_pad, d, d, qt, 0);
+    const char* ev = getenv("VQ_F32_TMA_VARIANT");
+    float* xt = nullptr;
+    if (ev && atoi(ev) >= 5) {  // k-major tiled copy of the corpus (n must be a multiple of 128 here)
+        cudaMalloc(&xt, f32_kmajor_bytes((int)n, d));
+        f32_queries_kmajor_launch(x, (int)n, d, d, xt, 0);
+        x = xt;
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
@@ -60,6 +67,7 @@ static void run_tma(const char* name, const float* q, int nq, const float* x, lo
     printf("%-40s %8.3f ms  %6.2f TFLOP/s (padded queries)  ctas=%d chunks=%d  rc=%d %s\n", name, best, flops / best / 1e9, plan.n_ctas, plan.n_chunks, rc,
            e == cudaSuccess ? "" : cudaGetErrorString(e));
     cudaFree(qt);
+    if (xt) cudaFree(xt);
 }
 
 int main(int argc, char** argv) {

@@ -54,6 +54,7 @@ struct DeviceGuard {
 struct vq_index {
     int d, dtype, device, ld, n_sms, variant;
     int kd, kdtype, seg;  // what the kernels contract over: kd columns of kdtype (VQ_F32X3: 6 segments of seg bf16 columns)
+    int kpad;             // VQ_F32: rows are stored as k-major tiles of 128 rows, [tile][kpad][128] floats (K1's TMA boxes)
     uint64_t capacity, ntotal;
     int64_t id_offset;
     void* data;
@@ -76,6 +77,8 @@ struct vq_index {
 
 static size_t esize(int dtype) { return dtype == VQ_F32 ? 4 : 2; }  // of one stored element (VQ_F32X3 stores bf16)
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+// bytes of the first `rows` rows of the corpus matrix (VQ_F32: whole 128-row tiles)
+static size_t storage_bytes(const vq_index* idx, uint64_t rows);
 static bool dtype_ok(int t) { return t == VQ_F32 || t == VQ_BF16 || t == VQ_F16; }  // of vectors crossing the ABI
 static bool storage_ok(int t) { return dtype_ok(t) || t == VQ_F32X3; }
 
@@ -134,15 +137,25 @@ static void host_copy(void* dst, const void* src, size_t bytes) {
     for (auto& th : pool) th.join();
 }
 
-// [n, d] rows of src_dtype -> the index's storage layout (corpus rows, or the query-side arrangement of VQ_F32X3)
-static int to_storage(const vq_index* idx, const void* src, int src_dtype, void* dst, long long n, int l2norm, int query_side, cudaStream_t s,
-                      long long n_pad = 0) {
+static size_t storage_bytes(const vq_index* idx, uint64_t rows) {
+    if (idx->dtype == VQ_F32) return (size_t)((rows + 127) / 128) * idx->kpad * 128 * sizeof(float);
+    return (size_t)rows * idx->ld * esize(idx->dtype);
+}
+
+// [n, d] rows of src_dtype -> rows row0 .. row0+n-1 of a matrix in the index's storage layout at `base` (the corpus, or a
+// query operand: the query-side arrangement of VQ_F32X3; VQ_F32: k-major tiles either way)
+static int to_storage(const vq_index* idx, const void* src, int src_dtype, void* base, uint64_t row0, long long n, int l2norm, int query_side,
+                      cudaStream_t s, long long n_pad = 0) {
+    if (idx->dtype == VQ_F32) return vq::tile_rows_launch(src, src_dtype, idx->d, (float*)base, (long long)row0, idx->kpad, n, idx->d, l2norm, s, n_pad);
+    void* dst = (uint8_t*)base + row0 * (size_t)idx->ld * esize(idx->dtype);
     if (idx->dtype == VQ_F32X3) return vq::split_rows_launch(src, src_dtype, idx->d, dst, idx->seg, n, idx->d, l2norm, query_side, s, n_pad);
     return vq::prep_rows_launch(src, src_dtype, idx->d, dst, idx->dtype, idx->ld, n, idx->d, l2norm, s, n_pad);
 }
 
-// stored corpus rows -> [n, d] rows of dst_dtype
-static int from_storage(const vq_index* idx, const void* src, void* dst, int dst_dtype, long long n, cudaStream_t s) {
+// stored corpus rows row0 .. row0+n-1 -> [n, d] rows of dst_dtype
+static int from_storage(const vq_index* idx, uint64_t row0, void* dst, int dst_dtype, long long n, cudaStream_t s) {
+    if (idx->dtype == VQ_F32) return vq::untile_rows_launch((const float*)idx->data, (long long)row0, idx->kpad, dst, dst_dtype, idx->d, n, idx->d, s);
+    const void* src = (const uint8_t*)idx->data + row0 * (size_t)idx->ld * esize(idx->dtype);
     if (idx->dtype == VQ_F32X3) return vq::join_rows_launch(src, idx->seg, dst, dst_dtype, idx->d, n, idx->d, s);
     return vq::prep_rows_launch(src, idx->dtype, idx->ld, dst, dst_dtype, idx->d, n, idx->d, 0, s);
 }
@@ -179,6 +192,7 @@ int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capac
     idx->kd = d;
     idx->kdtype = dtype;
     idx->seg = 0;
+    idx->kpad = dtype == VQ_F32 ? vq::f32_kpad(d) : 0;
     if (dtype == VQ_F32X3) {
         idx->seg = (d + 7) / 8 * 8;
         idx->ld = idx->kd = 6 * idx->seg;
@@ -196,11 +210,12 @@ int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capac
     idx->n_timed = 0;
     idx->launches = 0;
     if (capacity) {
-        cudaError_t e = cudaMalloc(&idx->data, capacity * idx->ld * esize(dtype));
+        cudaError_t e = cudaMalloc(&idx->data, storage_bytes(idx, capacity));
         if (e != cudaSuccess) {
             delete idx;
             return fail(VQ_ERR_NOMEM, "vq_index_create: cudaMalloc of %llu rows failed: %s", (unsigned long long)capacity, cudaGetErrorString(e));
         }
+        if (dtype == VQ_F32) cudaMemset(idx->data, 0, storage_bytes(idx, capacity));  // rows past ntotal of the last tile are read (and discarded)
         idx->capacity = capacity;
     }
     *out = idx;
@@ -288,15 +303,16 @@ static int grow(vq_index* idx, uint64_t need, cudaStream_t s) {
     uint64_t cap = idx->capacity ? idx->capacity : 1024;
     while (cap < need) cap += cap / 2 + 1;
     void* nd = nullptr;
-    const size_t row = (size_t)idx->ld * esize(idx->dtype);
-    cudaError_t e = cudaMalloc(&nd, cap * row);
+    cudaError_t e = cudaMalloc(&nd, storage_bytes(idx, cap));
     if (e != cudaSuccess && cap > need) {  // retry with the exact size
         cudaGetLastError();
         cap = need;
-        e = cudaMalloc(&nd, cap * row);
+        e = cudaMalloc(&nd, storage_bytes(idx, cap));
     }
     if (e != cudaSuccess) return fail(VQ_ERR_NOMEM, "vq_index_add: cudaMalloc of %llu rows failed: %s", (unsigned long long)cap, cudaGetErrorString(e));
-    if (idx->ntotal) CUDA_TRY(cudaMemcpyAsync(nd, idx->data, idx->ntotal * row, cudaMemcpyDeviceToDevice, s));
+    const size_t used = storage_bytes(idx, idx->ntotal);
+    if (used) CUDA_TRY(cudaMemcpyAsync(nd, idx->data, used, cudaMemcpyDeviceToDevice, s));
+    if (idx->dtype == VQ_F32) CUDA_TRY(cudaMemsetAsync((uint8_t*)nd + used, 0, storage_bytes(idx, cap) - used, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (idx->data) cudaFree(idx->data);
     idx->data = nd;
@@ -309,14 +325,15 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
     if (n == 0) return VQ_OK;
     // rows are uint32 in the candidate keys and int32 TMA coordinates in the tensor-core kernel
     if (idx->ntotal + n > 0x7FFFFF00ull) return fail(VQ_ERR_UNSUPPORTED, "vq_index_add: more than 2^31-256 rows per shard");
+    // fp32 exact mode: the k-major tiled matrix [tiles * kpad][128] is addressed with int32 TMA coordinates
+    if (idx->dtype == VQ_F32 && ((idx->ntotal + n + 127) / 128) * (uint64_t)idx->kpad > 0x7FFFFF00ull)
+        return fail(VQ_ERR_UNSUPPORTED, "vq_index_add: fp32 exact mode holds at most 2^31 / %d tiles of 128 rows per shard", idx->kpad);
     cudaStream_t s = (cudaStream_t)stream;
     VQ_ON_DEVICE(idx->device);
     int rc = grow(idx, idx->ntotal + n, s);
     if (rc) return rc;
-    const size_t row = (size_t)idx->ld * esize(idx->dtype);
-    uint8_t* dst = (uint8_t*)idx->data + idx->ntotal * row;
     if (is_device_ptr(x)) {
-        rc = to_storage(idx, x, src_dtype, dst, (long long)n, l2norm ? 2 : 0, 0, s);
+        rc = to_storage(idx, x, src_dtype, idx->data, idx->ntotal, (long long)n, l2norm ? 2 : 0, 0, s);
         if (rc) return fail(VQ_ERR_CUDA, "vq_index_add: prep kernel launch failed (%d)", rc);
     } else {
         // host source: pageable rows -> pinned buffer (host threads) -> device staging (DMA) -> conversion kernel,
@@ -339,7 +356,7 @@ int vq_index_add(vq_index* idx, const void* x, uint64_t n, int src_dtype, int l2
                 e = cudaMemcpyAsync(idx->stage[b], idx->pin[b], m * src_row, cudaMemcpyHostToDevice, s);
             }
             if (e == cudaSuccess) {
-                rc = to_storage(idx, idx->stage[b], src_dtype, dst + r0 * row, (long long)m, l2norm ? 2 : 0, 0, s);
+                rc = to_storage(idx, idx->stage[b], src_dtype, idx->data, idx->ntotal + r0, (long long)m, l2norm ? 2 : 0, 0, s);
                 if (rc == 0) e = cudaEventRecord(idx->ingest_ev[b], s);
             }
             if (e != cudaSuccess || rc) {
@@ -358,10 +375,8 @@ int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* ds
     if (n == 0) return VQ_OK;
     cudaStream_t s = (cudaStream_t)stream;
     VQ_ON_DEVICE(idx->device);
-    const size_t row = (size_t)idx->ld * esize(idx->dtype);
-    const uint8_t* src = (const uint8_t*)idx->data + start * row;
     if (is_device_ptr(dst)) {
-        int rc = from_storage(idx, src, dst, dst_dtype, (long long)n, s);
+        int rc = from_storage(idx, start, dst, dst_dtype, (long long)n, s);
         if (rc) return fail(VQ_ERR_CUDA, "vq_index_copy_rows: launch failed (%d)", rc);
         return VQ_OK;
     }
@@ -373,7 +388,7 @@ int vq_index_copy_rows(const vq_index* idx, uint64_t start, uint64_t n, void* ds
     CUDA_TRY(cudaMalloc(&stage, chunk * dst_row));
     for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
         const uint64_t m = (n - r0 < chunk) ? n - r0 : chunk;
-        int rc = from_storage(idx, src + r0 * row, stage, dst_dtype, (long long)m, s);
+        int rc = from_storage(idx, start + r0, stage, dst_dtype, (long long)m, s);
         cudaError_t e = rc ? cudaErrorUnknown : cudaMemcpyAsync((uint8_t*)dst + r0 * dst_row, stage, m * dst_row, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) {
@@ -495,7 +510,7 @@ static void make_plan(const vq_index* idx, int nq, SearchPlan* sp) {
     }
     size_t off = 0;
     sp->off_q = off;
-    off += align256((size_t)(nq > sp->nq_pad ? nq : sp->nq_pad) * idx->ld * esize(idx->dtype));
+    off += align256(storage_bytes(idx, (uint64_t)(nq > sp->nq_pad ? nq : sp->nq_pad)));
     sp->off_lists = off;
     off += align256((size_t)(1 + sp->pass_sets) * sp->nq_pad * VQ_CAP * sizeof(uint64_t));
     sp->off_counts = off;
@@ -558,7 +573,7 @@ static int search_round(vq_index* idx, const SearchPlan& sp, uint8_t* ws, const 
     } else if (sp.kind == 0) {
         for (int p = 0; p < sp.n_passes && !rc; p++) {
             const bool last = p == sp.n_passes - 1;
-            rc = vq::f32_topk_launch((const float*)qprep, nq, idx->ld, (const float*)idx->data, ntot, idx->ld, idx->d, k, sp.f32[p],
+            rc = vq::f32_topk_launch((const float*)qprep, nq, (const float*)idx->data, ntot, idx->d, k, sp.f32[p],
                                      sp.tile_b[p], sp.tile_b[p + 1], sp.stride[p], p ? sp.ratio : 0, p ? thr : nullptr, ub_score, ub_row,
                                      lists + (size_t)sp.nq_pad * VQ_CAP, counts + sp.nq_pad, s);
             const int expected = p == 0 ? (sp.tile_b[1] - sp.tile_b[0]) * 128 + k : 2048;
@@ -589,7 +604,7 @@ int vq_index_search(vq_index* idx, const void* q, int nq, int q_dtype, int l2nor
     void* qprep = ws + sp.off_q;
     // rows [nq, nq_pad) of the prepared query matrix are real zero rows (written by the same kernel), so the tensor-core
     // path never depends on TMA out-of-bounds fill for the query operand
-    int rc = to_storage(idx, q, q_dtype, qprep, nq, l2norm_q ? 1 : 0, 1, s, sp.nq_pad);
+    int rc = to_storage(idx, q, q_dtype, qprep, 0, nq, l2norm_q ? 1 : 0, 1, s, sp.nq_pad);
     if (rc) return fail(VQ_ERR_CUDA, "vq_index_search: query prep launch failed (%d)", rc);
     idx->launches += 1;
     const bool timed = idx->timing && idx->n_timed < VQ_TIMING_SLOTS && idx->ntotal;

@@ -81,8 +81,16 @@ struct F32Plan {
     int m_tiles, n_tiles, n_chunks, tiles_per_chunk, nq_pad, n_ctas;
 };
 void f32_plan(int nq, long long n_rows, int n_sms, F32Plan* plan);
-// one pass over corpus tiles (128 rows each) [tile_begin, tile_end); plan from f32_plan(nq, (tile_end - tile_begin) * 128 rows)
-int f32_topk_launch(const float* q, int nq, int ld_q, const float* x, long long n_rows, int ld_x, int d, int k,
+// K1's operands are K-MAJOR tiles of 128 rows: [tile][kpad][128] floats, kpad = f32_kpad(d) (d rounded up to 32, zero columns)
+int f32_kpad(int d);
+// [n][d] rows of src_dtype -> rows row0 .. row0+n-1 of a tiled matrix (+ zero rows up to n_pad); cast/L2norm as prep_rows_launch
+int tile_rows_launch(const void* src, int src_dtype, long long ld_src, float* dst, long long row0, int kpad, long long n, int d, int l2norm,
+                     cudaStream_t stream, long long n_pad = 0);
+// rows row0 .. row0+n-1 of a tiled matrix -> [n][ld_dst] rows of dst_dtype
+int untile_rows_launch(const float* src, long long row0, int kpad, void* dst, int dst_dtype, long long ld_dst, long long n, int d, cudaStream_t stream);
+// one pass over corpus tiles (128 rows each) [tile_begin, tile_end); plan from f32_plan(nq, (tile_end - tile_begin) * 128 rows);
+// qt: the prepared queries as plan.m_tiles tiles, xt: the corpus tiles
+int f32_topk_launch(const float* qt, int nq, const float* xt, long long n_rows, int d, int k,
                     const F32Plan& plan, int tile_begin, int tile_end, int map_stride, int map_ratio, const float* init_thr,
                     const float* ub_score, const uint32_t* ub_row, uint64_t* lists, int* counts, cudaStream_t stream);
 

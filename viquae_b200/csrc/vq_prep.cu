@@ -182,6 +182,118 @@ int join_rows_launch(const void* src, int seg, void* dst, int dst_dtype, long lo
     return e == cudaSuccess ? 0 : -(int)e;
 }
 
+// ---- fp32 exact mode: K-MAJOR tiles of 128 rows, [tile][kpad][128] floats (what K1's TMA boxes read, vq_fp32.cu).
+// Element (row R, column c) lives at ((R >> 7) * kpad + c) * 128 + (R & 127); columns d..kpad-1 are zero.
+// tile_rows: rows [0, n) of src become rows row0 .. row0+n-1 of the tiled matrix (rows [n, n_pad): zero rows); same cast
+// and normalisation ARITHMETIC as prep_rows_kernel (lane-strided fmaf sum, xor-shuffle tree), so an fp32 index holds the
+// same bits in either layout.  32 rows per CTA pass through a shared-memory transpose: loads coalesced along a row, stores
+// 128 bytes of 32 neighbouring rows at one column.
+template <typename S>
+__global__ void __launch_bounds__(256)
+tile_rows_kernel(const S* __restrict__ src, long long ld_src, float* __restrict__ dst, long long row0, int kpad, long long n, int d, int l2norm,
+                 long long n_pad) {
+    __shared__ float tile[32][33];
+    __shared__ float div_s[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long rb = blockIdx.x; rb * 32 < n_pad; rb += gridDim.x) {
+        for (int rr = warp; rr < 32; rr += 8) {
+            const long long r = rb * 32 + rr;
+            float div = 1.0f;
+            if (l2norm && r < n) {
+                const S* s = src + r * ld_src;
+                float acc = 0.0f;
+                for (int j = lane; j < d; j += 32) {
+                    const float v = to_f32<S>(s[j]);
+                    acc = fmaf(v, v, acc);
+                }
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(VQ_FULL_MASK, acc, o2);
+                div = sqrtf(acc);
+                if (l2norm == 2 && div == 0.0f) div = 1.0f;  // FAISS: zero vectors stay zero
+            }
+            if (lane == 0) div_s[rr] = div;
+        }
+        __syncthreads();
+        for (int k0 = 0; k0 < kpad; k0 += 32) {
+            for (int rr = warp; rr < 32; rr += 8) {
+                const long long r = rb * 32 + rr;
+                const int c = k0 + lane;
+                float v = 0.0f;
+                if (r < n && c < d) {
+                    v = to_f32<S>(src[r * ld_src + c]);
+                    if (l2norm) v = v / div_s[rr];  // l2norm == 1: 0/0 -> NaN like numpy
+                }
+                tile[rr][lane] = v;
+            }
+            __syncthreads();
+            const long long r = rb * 32 + lane;
+            if (r < n_pad) {
+                const long long R = row0 + r;
+                float* o = dst + ((R >> 7) * kpad + k0) * 128 + (R & 127);
+                for (int kk = warp; kk < 32; kk += 8) o[(long long)kk * 128] = tile[lane][kk];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// rows row0 .. row0+n-1 of the tiled matrix -> [n][ld_dst] rows of D (columns < d)
+template <typename D>
+__global__ void __launch_bounds__(256)
+untile_rows_kernel(const float* __restrict__ src, long long row0, int kpad, D* __restrict__ dst, long long ld_dst, long long n, int d) {
+    __shared__ float tile[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long rb = blockIdx.x; rb * 32 < n; rb += gridDim.x) {
+        for (int k0 = 0; k0 < d; k0 += 32) {
+            const long long r = rb * 32 + lane;
+            if (r < n) {
+                const long long R = row0 + r;
+                const float* s = src + ((R >> 7) * kpad + k0) * 128 + (R & 127);
+                for (int kk = warp; kk < 32; kk += 8) tile[lane][kk] = s[(long long)kk * 128];
+            }
+            __syncthreads();
+            for (int rr = warp; rr < 32; rr += 8) {
+                const long long r2 = rb * 32 + rr;
+                const int c = k0 + lane;
+                if (r2 < n && c < d) dst[r2 * ld_dst + c] = from_f32<D>(tile[rr][lane]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+int tile_rows_launch(const void* src, int src_dtype, long long ld_src, float* dst, long long row0, int kpad, long long n, int d, int l2norm,
+                     cudaStream_t stream, long long n_pad) {
+    if (n_pad < n) n_pad = n;
+    long long blocks = (n_pad + 31) / 32;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) return 0;
+    switch (src_dtype) {
+        case VQ_DTYPE_F32: tile_rows_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>((const float*)src, ld_src, dst, row0, kpad, n, d, l2norm, n_pad); break;
+        case VQ_DTYPE_BF16:
+            tile_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)src, ld_src, dst, row0, kpad, n, d, l2norm, n_pad);
+            break;
+        case VQ_DTYPE_F16: tile_rows_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)src, ld_src, dst, row0, kpad, n, d, l2norm, n_pad); break;
+        default: return -2;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+int untile_rows_launch(const float* src, long long row0, int kpad, void* dst, int dst_dtype, long long ld_dst, long long n, int d, cudaStream_t stream) {
+    long long blocks = (n + 31) / 32;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) return 0;
+    switch (dst_dtype) {
+        case VQ_DTYPE_F32: untile_rows_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(src, row0, kpad, (float*)dst, ld_dst, n, d); break;
+        case VQ_DTYPE_BF16: untile_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(src, row0, kpad, (__nv_bfloat16*)dst, ld_dst, n, d); break;
+        case VQ_DTYPE_F16: untile_rows_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>(src, row0, kpad, (__half*)dst, ld_dst, n, d); break;
+        default: return -2;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
 int prep_rows_launch(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
                      long long n, int d, int l2norm, cudaStream_t stream, long long n_pad) {
     switch (src_dtype) {
