@@ -60,6 +60,48 @@ def test_fp32_mode_is_bit_exact(N, nq, d, k):
     assert np.array_equal(np.asarray(res.total_scores).view(np.uint32), Dr.view(np.uint32)), "fixed reduction order: scores bit-exact"
 
 
+@pytest.mark.parametrize("d", [100, 33, 768])
+def test_fp32_tiled_storage_ragged_adds_reconstruct_and_l2norm(d, tmp_path):
+    """The fp32 exact mode keeps its rows as k-major tiles of 128 rows (what K1's TMA boxes read): appends that start and
+    end inside a tile, growth across reallocations, d not a multiple of the 32-column k block, reconstruct / save / load
+    giving back the exact bits, device-resident sources, and the ingest-side L2 normalisation producing the same bits as
+    the row-major prep kernel behind vq_prep_rows."""
+    from viquae_b200 import _lib
+    from viquae_b200.index import B200FlatIndex
+    X, Q = make(1500, 37, d, "f32", seed=5)
+    idx = B200FlatIndex(d=d, dtype="f32")
+    cuts = [0, 77, 78, 377, 1024, 1153, 1500]   # ragged appends: inside a tile, exactly to a tile edge, across several tiles
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if (a // 100) % 2:
+            idx.add(torch.from_numpy(X[a:b]).cuda())     # device-resident source
+        else:
+            idx.add(X[a:b])                               # host source through the pinned pipeline
+    assert len(idx) == 1500
+    assert np.array_equal(idx.reconstruct_n(0, None).view(np.uint32), X.view(np.uint32))
+    assert np.array_equal(idx.reconstruct_n(120, 20).view(np.uint32), X[120:140].view(np.uint32))   # a window across a tile edge
+    for k in (1, 10):
+        res = idx.search_batch(Q, k)
+        Dr, Ir = c_oracle.flat_ip(Q, X, k)
+        assert np.array_equal(np.asarray(res.total_indices), Ir)
+        assert np.array_equal(np.asarray(res.total_scores).view(np.uint32), Dr.view(np.uint32))
+    idx.save(tmp_path / "f32.index")
+    idx2 = B200FlatIndex.load(tmp_path / "f32.index")
+    r1, r2 = idx.search_batch(Q, 10), idx2.search_batch(Q, 10)
+    assert np.array_equal(r1.total_indices, r2.total_indices) and np.array_equal(r1.total_scores, r2.total_scores)
+    idx.close(); idx2.close()
+    # L2norm on ingest: same bits as the row-major prep kernel (one zero row stays zero, FAISS semantics)
+    Xz = X[:300].copy(); Xz[17] = 0.0
+    idn = B200FlatIndex(d=d, dtype="f32", string_factory="L2norm,Flat")
+    idn.add(Xz)
+    src = torch.from_numpy(Xz).cuda()
+    ref = torch.empty_like(src)
+    _lib.check(_lib.load().vq_prep_rows(src.data_ptr(), _lib.F32, ref.data_ptr(), _lib.F32, 300, d, 2, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(idn.reconstruct_n(0, None).view(np.uint32), ref.cpu().numpy().view(np.uint32))
+    assert not np.any(idn.reconstruct_n(17, 1))
+    idn.close()
+
+
 @pytest.mark.parametrize("variant,N,nq,d,k,dtype", [
     ("tc_cg1", 5000, 70, 768, 100, "bf16"),
     ("tc_cg1", 70001, 100, 768, 100, "bf16"),
