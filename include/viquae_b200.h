@@ -53,7 +53,9 @@ const char* vq_version(void);
 
 /* faiss.IndexFlat(d, faiss.METRIC_INNER_PRODUCT)            [datasets/search.py:276-288]
  * `dtype` is the STORAGE type of the corpus on the device (VQ_F32 = exact fixed-order mode, VQ_BF16 / VQ_F16 =
- * tensor-core mode on rounded embeddings, VQ_F32X3 = tensor-core mode on split fp32 embeddings); `capacity` pre-sizes the device buffer in rows (it grows on demand). */
+ * tensor-core mode on rounded embeddings, VQ_F32X3 = tensor-core mode on split fp32 embeddings); `capacity` pre-sizes the device buffer in rows (it grows on demand).
+ * The device layout is the engine's own (VQ_F32: k-major tiles of 128 rows, d padded to a multiple of 32; VQ_F32X3:
+ * six bf16 segments per row); rows always cross this interface as plain [n, d] row-major arrays. */
 int vq_index_create(vq_index** out, int d, int dtype, int device, uint64_t capacity);
 void vq_index_destroy(vq_index* idx);
 
