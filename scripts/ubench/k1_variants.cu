@@ -6,6 +6,7 @@
 #include <vector>
 #include <algorithm>
 #include "k1_experiments.cuh"
+#include "k1_wide.cuh"
 
 using namespace vq;
 
@@ -70,6 +71,53 @@ static void run_tma(const char* name, const float* q, int nq, const float* x, lo
     if (xt) cudaFree(xt);
 }
 
+static int encode_kmajor(CUtensorMap* m, const void* base, uint64_t tiles, int kpad) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    auto enc = reinterpret_cast<PFN_encodeTiled>(ptr);
+    cuuint64_t gdim[2] = {128, tiles * (uint64_t)kpad};
+    cuuint64_t gstride[1] = {512};
+    cuuint32_t box[2] = {128, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return (int)enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+static void run_wide(const char* name, const float* q, int nq, const float* x, long long n, int d, const float* thr, int sms) {
+    if (!((g_mask >> g_idx++) & 1)) return;
+    F32Plan plan;
+    f32_plan_wide(nq, n, sms, &plan);
+    const int n_tiles = (int)((n + 127) / 128), kpad = (d + 31) / 32 * 32;
+    float *qt, *xt; uint64_t* lists; int* counts;
+    cudaMalloc(&qt, f32_kmajor_bytes(plan.nq_pad, d));
+    cudaMalloc(&xt, f32_kmajor_bytes((int)n, d));
+    cudaMalloc(&lists, (size_t)plan.n_chunks * plan.nq_pad * VQ_CAP * 8);
+    cudaMalloc(&counts, (size_t)plan.n_chunks * plan.nq_pad * 4);
+    f32_queries_kmajor_launch(q, plan.nq_pad, d, d, qt, 0);
+    f32_queries_kmajor_launch(x, (int)n, d, d, xt, 0);
+    CUtensorMap tq, tx;
+    int rc = encode_kmajor(&tq, qt, plan.nq_pad / 128, kpad) | encode_kmajor(&tx, xt, n_tiles, kpad);
+    cudaFuncSetAttribute(f32w::f32_topk_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32w::SMEM_BYTES);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < g_reps; rep++) {
+        cudaEventRecord(e0);
+        f32w::f32_topk_wide_kernel<<<plan.n_ctas, f32w::THREADS, f32w::SMEM_BYTES>>>(tq, tx, nq, n, d, 100, plan.m_tiles, 0, n_tiles, 1, 0, plan.n_chunks,
+                                                                                    plan.tiles_per_chunk, plan.nq_pad, thr, nullptr, nullptr, lists, counts);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if ((rep || g_reps == 1) && ms < best) best = ms;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    const double flops = 2.0 * plan.nq_pad * (double)n * d;
+    printf("%-40s %8.3f ms  %6.2f TFLOP/s (padded queries)  ctas=%d chunks=%d  rc=%d %s\n", name, best, flops / best / 1e9, plan.n_ctas, plan.n_chunks, rc,
+           e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(qt); cudaFree(xt); cudaFree(lists); cudaFree(counts);
+}
+
 int main(int argc, char** argv) {
     const int nq = argc > 1 ? atoi(argv[1]) : 1280, d = 768;
     const long long n = argc > 2 ? atoll(argv[2]) : 148LL * 2 * 128 * 16;
@@ -107,6 +155,7 @@ int main(int argc, char** argv) {
     run<true, true, true, true>("FFMA2 lean-loads    4x8  swizzled", q, nq, x, n, d, thr, lists, counts, sms);
     setenv("VQ_F32_TMA_VARIANT", argc > 5 ? argv[5] : "0", 1);
     run_tma("FFMA2 TMA-fed, 3 x 32-column stages", q, nq, x, n, d, thr, lists, counts, sms);
+    run_wide("FFMA2 TMA k-major 256x128, 16x8/thread, 1 CTA/SM", q, nq, x, n, d, thr, sms);
     run<false, true, false, false, false>("FFMA  NO staging    2x16 padded", q, nq, x, n, d, thr, lists, counts, sms);
     run<true, true, false, false, false>("FFMA2 NO staging    2x16 padded", q, nq, x, n, d, thr, lists, counts, sms);
     run<false, true, true, true, false>("FFMA  NO staging    4x8  swizzled", q, nq, x, n, d, thr, lists, counts, sms);
