@@ -150,6 +150,43 @@ def test_wsum_union_and_order():
     assert z["q"]["1"] == 0.0  # single result: std 0 -> denominator 1e-9
 
 
+def test_fusion_oracle_against_independent_referees():
+    """ranx is not installable here, so zmuv / min-max / wsum are restated from its published definitions (parity
+    unpinned).  Narrowed with referees that share no code with oracle/fuse_oracle.py: scikit-learn's StandardScaler
+    (population std) and MinMaxScaler per query for the two normalisations, a pandas outer-join for the weighted sum
+    over the union of documents, and a stable numpy sort for the ranking."""
+    import pandas as pd
+    from sklearn.preprocessing import MinMaxScaler, StandardScaler
+
+    rng = np.random.default_rng(11)
+    runs = []
+    for r in range(3):
+        run = {}
+        for q in range(7):
+            docs = rng.choice(60, size=int(rng.integers(2, 25)), replace=False)
+            run[q] = {int(d): float(s) for d, s in zip(docs, rng.normal(70 - 30 * r, 2 + r, size=len(docs)))}
+        runs.append(run)
+    for name, scaler in (("zmuv", StandardScaler), ("min-max", MinMaxScaler)):
+        got = fuse_oracle.NORMS[name](runs[0])
+        for q, results in runs[0].items():
+            ref = scaler().fit_transform(np.array(list(results.values()), dtype=np.float64)[:, None])[:, 0]
+            assert np.allclose(np.array([got[q][d] for d in results]), ref, rtol=1e-12, atol=1e-12), (name, q)
+    weights = [0.5, 0.3, 0.2]
+    fused = fuse_oracle.fuse(runs, weights, norm="zmuv", defmin=False)
+    normed = [fuse_oracle.zmuv_norm(r) for r in runs]
+    for q in range(7):
+        frame = pd.concat([pd.Series(n[q], name=i, dtype=np.float64) for i, n in enumerate(normed)], axis=1).fillna(0.0)
+        ref = (frame * weights).sum(axis=1)                      # a run that lacks a document contributes nothing
+        ref = ref.sort_index().sort_values(ascending=False, kind="stable")   # descending score, ties by ascending doc id
+        assert list(fused[q].keys()) == [int(d) for d in ref.index]
+        assert np.allclose(np.array(list(fused[q].values())), ref.to_numpy(), rtol=1e-12, atol=1e-12)
+    # default-minimum then gzmuv (the reference's own functions, pinned by the golden fixtures) keep the union complete
+    filled = fuse_oracle.default_minimum(runs)
+    for q in range(7):
+        union = set().union(*[set(r[q]) for r in runs])
+        assert all(set(f[q]) == union for f in filled)
+
+
 def test_f32x3_split_is_exact_and_six_terms_are_fp32_faithful():
     """The VQ_F32X3 layout on the CPU: three bf16 terms reproduce every fp32 value exactly, and the six product
     terms the tensor cores accumulate miss the exact inner product by less than 2^-23 of sum |q_j x_j|."""
