@@ -69,10 +69,13 @@ def test_fp32_tiled_storage_ragged_adds_reconstruct_and_l2norm(d, tmp_path):
     from viquae_b200 import _lib
     from viquae_b200.index import B200FlatIndex
     X, Q = make(1500, 37, d, "f32", seed=5)
+    X[1153:] = flat_ip.bf16_round(X[1153:])      # the last append arrives as a bf16 tensor (exact in fp32)
     idx = B200FlatIndex(d=d, dtype="f32")
     cuts = [0, 77, 78, 377, 1024, 1153, 1500]   # ragged appends: inside a tile, exactly to a tile edge, across several tiles
     for a, b in zip(cuts[:-1], cuts[1:]):
-        if (a // 100) % 2:
+        if a == 1153:
+            idx.add(torch.from_numpy(X[a:b]).cuda().to(torch.bfloat16))   # 16-bit device source, widened on ingest
+        elif (a // 100) % 2:
             idx.add(torch.from_numpy(X[a:b]).cuda())     # device-resident source
         else:
             idx.add(X[a:b])                               # host source through the pinned pipeline
