@@ -380,7 +380,7 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
         mbar_arrive_expect_tx(&full_bar[p_stage], STAGE_BYTES);
         const uint32_t dst = ring + p_stage * STAGE_BYTES;
         tma_load_2d(&tmap_qt, &full_bar[p_stage], dst, 0, hot ? 0 : pc.qrow + pc.kb * BK);
-        if (VAR == 5) tma_load_2d(&tmap_x, &full_bar[p_stage], dst + A_BYTES, 0, hot ? 0 : (pc.xrow / BN) * kpad + pc.kb * BK);
+        if (VAR >= 5) tma_load_2d(&tmap_x, &full_bar[p_stage], dst + A_BYTES, 0, hot ? 0 : (pc.xrow / BN) * kpad + pc.kb * BK);
         else tma_load_2d(&tmap_x, &full_bar[p_stage], dst + A_BYTES, hot ? 0 : pc.kb * BK, hot ? 0 : pc.xrow);
     };
     auto p_next = [&]() {
@@ -422,10 +422,14 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
         for (int t = t0; t < t1; t++) {
             const long long x0 = phys_row(t);
             unsigned long long acc2[4][8];
+            float facc[4][8][2];
 #pragma unroll
             for (int p = 0; p < 4; p++)
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc2[p][j] = 0ull;
+                for (int j = 0; j < 8; j++) {
+                    acc2[p][j] = 0ull;
+                    facc[p][j][0] = facc[p][j][1] = 0.0f;
+                }
 
             for (int kb = 0; kb < num_kb; kb++, it++) {
                 // producer duty rotates over the warps: refill the stage every warp released one k block ago
@@ -440,7 +444,7 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
                     c_phase ^= 1;
                 }
                 const uint32_t As = ring + s * STAGE_BYTES + a_off, Bs = ring + s * STAGE_BYTES + A_BYTES + b_row;
-                if (VAR == 5) {
+                if (VAR >= 5) {
                     // both operands k-major: queries are the scalars, PAIRS of neighbouring corpus rows the packed operand
                     // (the inner loop of the register-staged kernel, fed by TMA)
                     const uint32_t Ak = ring + s * STAGE_BYTES + (uint32_t)ty * 16u, Bk = ring + s * STAGE_BYTES + A_BYTES + (uint32_t)tx * 16u;
@@ -453,10 +457,19 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
                         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                         const unsigned long long b[4] = {b0.x, b0.y, b1.x, b1.y};
                         // acc2[p][j] doubles as [pair of rows p][query j]: 4 x 8
+                        // VAR 7 / 8 / 9: only the first 1 / 2 / 0 pairs of rows go through FFMA2, the rest through scalar FFMA
+                        // (mixing the issue-cheap packed form with the pipe-cheap scalar form)
+                        constexpr int NP2 = VAR == 7 ? 1 : VAR == 8 ? 2 : VAR == 9 ? 0 : 4;
 #pragma unroll
                         for (int i = 0; i < 8; i++)
 #pragma unroll
-                            for (int p = 0; p < 4; p++) ffma2(acc2[p][i], a[i], b[p]);
+                            for (int p = 0; p < 4; p++) {
+                                if (p < NP2) ffma2(acc2[p][i], a[i], b[p]);
+                                else {
+                                    facc[p][i][0] = fmaf(a[i], __uint_as_float((uint32_t)b[p]), facc[p][i][0]);
+                                    facc[p][i][1] = fmaf(a[i], __uint_as_float((uint32_t)(b[p] >> 32)), facc[p][i][1]);
+                                }
+                            }
                     }
                 } else if (VAR == 2) {
                     // corpus operand two k at a time (LDS.64): 16 instead of 32 operand registers
@@ -532,8 +545,10 @@ f32_topk_tma_kernel(const __grid_constant__ CUtensorMap tmap_qt, const __grid_co
                 unsigned long long* list = reinterpret_cast<unsigned long long*>(item_lists + (size_t)r * VQ_CAP);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const long long xr = VAR == 5 ? x0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : x0 + tx + 16 * j;
-                    const float s = VAR == 5 ? __uint_as_float((j & 1) ? (uint32_t)(acc2[j >> 1][i] >> 32) : (uint32_t)acc2[j >> 1][i])
+                    constexpr int NP2E = VAR == 7 ? 1 : VAR == 8 ? 2 : VAR == 9 ? 0 : 4;
+                    const long long xr = VAR >= 5 ? x0 + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : x0 + tx + 16 * j;
+                    const float s = VAR >= 5 ? ((j >> 1) < NP2E ? __uint_as_float((j & 1) ? (uint32_t)(acc2[j >> 1][i] >> 32) : (uint32_t)acc2[j >> 1][i])
+                                                                : facc[j >> 1][i][j & 1])
                                              : __uint_as_float((i & 1) ? (uint32_t)(acc2[i >> 1][j] >> 32) : (uint32_t)acc2[i >> 1][j]);
                     if (xr < n_rows && s > thr && (s < ubs || (s == ubs && (uint32_t)xr > ubr))) {
                         const int pos = atomicAdd(&cnt_s[r], 1);
@@ -695,14 +710,15 @@ int f32_topk_tma_launch(const float* qt, int nq, const float* x, long long n_row
     if (var < 0) {
         const char* e = getenv("VQ_F32_TMA_VARIANT");
         var = e ? atoi(e) : 0;
-        if (var < 0 || var > 6) var = 0;
+        if (var < 0 || var > 9) var = 0;
         hot = getenv("VQ_F32_TMA_HOT") ? 1 : 0;
     }
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, int, int, long long, int, int, int, int, int, int, int, int, int, int, const float*, const float*,
                            const uint32_t*, uint64_t*, int*);
     kern_t kern = var == 0 ? T::f32_topk_tma_kernel<0, 2> : var == 1 ? T::f32_topk_tma_kernel<1, 2> : var == 2 ? T::f32_topk_tma_kernel<2, 2>
-                : var == 3 ? T::f32_topk_tma_kernel<3, 2> : var == 4 ? T::f32_topk_tma_kernel<0, 1> : var == 5 ? T::f32_topk_tma_kernel<5, 2> : T::f32_topk_tma_kernel<5, 1>;
-    static bool attr_set_dev[64][7] = {};  // cudaFuncSetAttribute is per device
+                : var == 3 ? T::f32_topk_tma_kernel<3, 2> : var == 4 ? T::f32_topk_tma_kernel<0, 1> : var == 5 ? T::f32_topk_tma_kernel<5, 2> : var == 6 ? T::f32_topk_tma_kernel<5, 1>
+                : var == 7 ? T::f32_topk_tma_kernel<7, 2> : var == 8 ? T::f32_topk_tma_kernel<8, 2> : T::f32_topk_tma_kernel<9, 2>;
+    static bool attr_set_dev[64][10] = {};  // cudaFuncSetAttribute is per device
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set_dev[dev_ & 63][var]) {
