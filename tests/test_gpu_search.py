@@ -441,6 +441,25 @@ def test_randomized_small_shapes_all_paths():
         idx.close()
 
 
+def test_fp32_exact_mode_fuzz_multi_pass_shapes():
+    """Seeded fuzz of the fp32 exact mode alone (TMA ring + k-major tiles): shapes with one or several priming passes, more
+    work items than CTAs and fewer, several query tiles, d around the 32-column k block — ids and score bits equal the
+    fixed-order C oracle every time."""
+    rng = np.random.default_rng(77)
+    shapes = [(40000, 300, 96, 100), (70001, 5, 33, 10), (20000, 641, 64, 7), (129, 129, 32, 128), (38000, 128, 31, 1),
+              (128, 1, 1, 1), (50000, 257, 40, 50), (9000, 700, 160, 20)]
+    for trial in range(10):
+        shapes.append((int(rng.integers(1, 30000)), int(rng.integers(1, 400)), int(rng.integers(1, 130)), int(rng.integers(1, 129))))
+    for trial, (N, nq, d, k) in enumerate(shapes):
+        X, Q = make(N, nq, d, "f32", seed=500 + trial)
+        idx = engine(X, "f32")
+        res = idx.search_batch(Q, k)
+        Dr, Ir = c_oracle.flat_ip(Q, X, k)
+        assert np.array_equal(np.asarray(res.total_indices), Ir), (trial, N, nq, d, k)
+        assert np.array_equal(np.asarray(res.total_scores).view(np.uint32), Dr.view(np.uint32)), (trial, N, nq, d, k)
+        idx.close()
+
+
 def test_knowledgebase_save_path_then_load(tmp_path):
     """`save_path` / `load` of the index config (meerqat/ir/search.py:234-248), through KnowledgeBase."""
     from viquae_b200.search import KnowledgeBase
