@@ -469,6 +469,9 @@ def roofline(args, dtype, nq, local_rows, kern_ms, world, rows):
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["peak_source"] = (f"{peaks_src} (MEASURED_PEAKS.json burst figure: kernel timed alone)" if peaks_src == "measured"
                            else "fallback (B200_PROFILING.md)")
+    if dtype == "f32":  # no measured figure for the FMA pipe: the nominal issue rate at the max SM clock; a pure-FFMA microbenchmark
+        # (scripts/ubench/ffma2_rate.cu) reaches 0.97 of it, a pure-FFMA2 one 0.87
+        roof["peak_source"] = "nominal: 148 SMs x 128 FMA/clk x 2 flop x max SM clock"
     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch(es), from the committed
     # `ncu --set full` capture of this same workload (profiles/traffic.json); null for other workloads
     roof["traffic"] = None
